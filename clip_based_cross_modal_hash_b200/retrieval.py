@@ -1,0 +1,371 @@
+"""Host side of the bit-packed retrieval evaluator: torch tensors in, libcmh.so kernels underneath.
+
+Everything here works on CUDA tensors and launches on torch's current stream.  torch is plumbing only
+(device memory, streams, ``torch.distributed``); all arithmetic happens in the kernels of
+``csrc/cmh_retrieval.cu`` / ``csrc/cmh_pack.cu`` through the C ABI of ``include/cmh.h``.
+
+Stage functions (``hist`` -> ``scan`` -> ``rank_map`` / ``rank_topk`` -> ``map_finish`` / ``topk_merge``)
+mirror the C entry points one to one; ``map_k`` / ``topk`` chain them for one GPU and
+``ShardedEvaluator`` chains them across the ranks of a process group with the gallery sharded by
+contiguous index range.
+
+Reference being replaced: ``common/calc_utils.py:51-92`` (calc_hammingDist, calc_map_k) and the fp32 +-1
+code buffers / all-reduce of ``runners/base.py:242-266``.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import CmhError, Plan, check
+
+EMPTY_KEY = -1  # 0xFFFF_FFFF_FFFF_FFFF viewed as int64
+_LABEL_DT = {torch.int64: 0, torch.float32: 1, torch.uint8: 2, torch.bool: 2, torch.int32: 3}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise CmhError("expected a CUDA tensor (there is no CPU path)")
+        if dev is not None and t.device != dev:
+            raise CmhError("tensors live on different devices")
+        dev = t.device
+    return dev
+
+
+def code_words(nbits: int) -> int:
+    w = _lib.lib().cmh_code_words(nbits)
+    if w < 0:
+        raise CmhError("code length %d not supported (1..128 bits)" % nbits)
+    return w
+
+
+def label_words(ncls: int) -> int:
+    w = _lib.lib().cmh_label_words(ncls)
+    if w < 0:
+        raise CmhError("%d classes not supported (0..128)" % ncls)
+    return w
+
+
+# ---------------------------------------------------------------------------------------------------------
+# R0 packing
+# ---------------------------------------------------------------------------------------------------------
+def new_bad_counter(device) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.int64, device=device)
+
+
+def pack_codes(codes: torch.Tensor, bad: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n, K] fp32 (+-1) CUDA -> [n, W] int32 (uint32 bit patterns).  ``bad`` (int64[1], device) counts
+    elements that are not exactly +-1 (it is added to, not reset)."""
+    _need_cuda(codes, bad)
+    if codes.dim() != 2:
+        raise CmhError("codes must be [n, K]")
+    if codes.dtype != torch.float32:
+        codes = codes.to(torch.float32)
+    if codes.stride(1) != 1:
+        codes = codes.contiguous()
+    n, nbits = codes.shape
+    out = torch.empty((n, code_words(nbits)), dtype=torch.int32, device=codes.device)
+    with torch.cuda.device(codes.device):
+        check(_lib.lib().cmh_pack_codes_f32(codes.data_ptr(), n, nbits, codes.stride(0) if n > 1 else nbits,
+                                            out.data_ptr(), _ptr(bad), _stream()))
+    return out
+
+
+def pack_labels(labels: torch.Tensor, bad: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n, C] multi-hot (int64 / int32 / uint8 / bool / fp32) CUDA -> [n, LW] int32."""
+    _need_cuda(labels, bad)
+    if labels.dim() != 2:
+        raise CmhError("labels must be [n, C]")
+    if labels.dtype not in _LABEL_DT:
+        labels = labels.to(torch.float32)
+    if labels.stride(1) != 1:
+        labels = labels.contiguous()
+    n, ncls = labels.shape
+    lw = label_words(ncls)
+    if lw == 0:
+        raise CmhError("labels need at least one class")
+    out = torch.empty((n, lw), dtype=torch.int32, device=labels.device)
+    with torch.cuda.device(labels.device):
+        check(_lib.lib().cmh_pack_labels(labels.data_ptr(), _LABEL_DT[labels.dtype], n, ncls,
+                                         labels.stride(0) if n > 1 else ncls, out.data_ptr(), _ptr(bad), _stream()))
+    return out
+
+
+def unpack_codes(packed: torch.Tensor, nbits: int) -> torch.Tensor:
+    """[n, W] int32 -> [n, K] fp32 +-1 (the reference's code format)."""
+    _need_cuda(packed)
+    n = packed.shape[0]
+    out = torch.empty((n, nbits), dtype=torch.float32, device=packed.device)
+    with torch.cuda.device(packed.device):
+        check(_lib.lib().cmh_unpack_codes_f32(packed.data_ptr(), n, nbits, out.data_ptr(), nbits, _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# R1 materialised Hamming matrix (calc_hammingDist)
+# ---------------------------------------------------------------------------------------------------------
+def hamming_matrix(qp: torch.Tensor, gp: torch.Tensor, nbits: int) -> torch.Tensor:
+    _need_cuda(qp, gp)
+    Q, N = qp.shape[0], gp.shape[0]
+    out = torch.empty((Q, N), dtype=torch.float32, device=qp.device)
+    with torch.cuda.device(qp.device):
+        check(_lib.lib().cmh_hamming_f32(qp.data_ptr(), Q, gp.data_ptr(), N, nbits, out.data_ptr(), N, _stream()))
+    return out
+
+
+def hamming_dense(b1: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    _need_cuda(b1, b2)
+    b1 = b1.to(torch.float32).contiguous()
+    b2 = b2.to(torch.float32).contiguous()
+    Q, K = b1.shape
+    N = b2.shape[0]
+    out = torch.empty((Q, N), dtype=torch.float32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        check(_lib.lib().cmh_hamming_dense_f32(b1.data_ptr(), Q, b2.data_ptr(), N, K, out.data_ptr(), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# evaluator stages (one C entry point each)
+# ---------------------------------------------------------------------------------------------------------
+class CudaStages:
+    """The product's stage kernels.  ``ShardedEvaluator`` takes any object with these methods so that the
+    exchange logic can be exercised on CPU (gloo) in tests with an oracle-backed stand-in."""
+
+    def make_plan(self, Q, N, nbits, ncls, N_geom=None, target_blocks=0) -> Plan:
+        return _lib.make_plan(Q, N, nbits, ncls, N_geom, target_blocks)
+
+    def hist(self, plan: Plan, qp, qlp, gp, glp) -> torch.Tensor:
+        dev = _need_cuda(qp, qlp, gp, glp)
+        hist = torch.empty((plan.nchunks, plan.bins, plan.Qpad), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_hist(ctypes.byref(plan), qp.data_ptr(), _ptr(qlp), gp.data_ptr(), _ptr(glp),
+                                      hist.data_ptr(), _stream()))
+        return hist
+
+    def scan(self, plan: Plan, hist_all: torch.Tensor, world: int, rank: int, k: Optional[int],
+             with_rel: bool = True) -> Dict[str, torch.Tensor]:
+        dev = _need_cuda(hist_all)
+        shape = (plan.nchunks, plan.bins, plan.Qpad)
+        o = {
+            "within_all": torch.empty(shape, dtype=torch.int32, device=dev),
+            "below_all": torch.empty((plan.bins, plan.Qpad), dtype=torch.int32, device=dev),
+            "within_rel": torch.empty(shape, dtype=torch.int32, device=dev) if with_rel else None,
+            "below_rel": torch.empty((plan.bins, plan.Qpad), dtype=torch.int32, device=dev) if with_rel else None,
+            "tsum": torch.empty(plan.Qpad, dtype=torch.int32, device=dev),
+            "total": torch.empty(plan.Qpad, dtype=torch.int32, device=dev),
+            "thresh": torch.empty(plan.Qpad, dtype=torch.int32, device=dev),
+        }
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_scan(ctypes.byref(plan), hist_all.data_ptr(), world, rank, int(k) if k else 0,
+                                      o["within_all"].data_ptr(), _ptr(o["within_rel"]), o["below_all"].data_ptr(),
+                                      _ptr(o["below_rel"]), o["tsum"].data_ptr(), o["total"].data_ptr(),
+                                      o["thresh"].data_ptr(), _stream()))
+        return o
+
+    def rank_map(self, plan: Plan, qp, qlp, gp, glp, sc: Dict[str, torch.Tensor],
+                 tindex: Optional[torch.Tensor] = None) -> torch.Tensor:
+        dev = _need_cuda(qp, qlp, gp, glp, tindex)
+        ap_partial = torch.empty((plan.nchunks, plan.Qpad), dtype=torch.float64, device=dev)
+        cap = 0
+        if tindex is not None:
+            if tindex.dtype != torch.int32 or tindex.dim() != 2 or tindex.shape[0] < plan.Q or not tindex.is_contiguous():
+                raise CmhError("tindex must be a contiguous int32 [Q, cap] tensor")
+            cap = tindex.shape[1]
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_rank_map(ctypes.byref(plan), qp.data_ptr(), qlp.data_ptr(), gp.data_ptr(),
+                                          glp.data_ptr(), sc["within_all"].data_ptr(), sc["within_rel"].data_ptr(),
+                                          sc["below_all"].data_ptr(), sc["below_rel"].data_ptr(),
+                                          sc["total"].data_ptr(), ap_partial.data_ptr(), _ptr(tindex), cap, _stream()))
+        return ap_partial
+
+    def map_finish(self, plan: Plan, ap_partial_all: torch.Tensor, total: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        dev = _need_cuda(ap_partial_all, total)
+        ap = torch.empty(plan.Q, dtype=torch.float64, device=dev)
+        out = torch.empty((), dtype=torch.float64, device=dev)
+        nparts = ap_partial_all.numel() // plan.Qpad
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_map_finish(ctypes.byref(plan), ap_partial_all.data_ptr(), nparts, total.data_ptr(),
+                                            ap.data_ptr(), out.data_ptr(), _stream()))
+        return ap, out
+
+    def rank_topk(self, plan: Plan, qp, gp, sc: Dict[str, torch.Tensor], k: int, idx_offset: int,
+                  keys: Optional[torch.Tensor] = None) -> torch.Tensor:
+        dev = _need_cuda(qp, gp)
+        if keys is None:
+            keys = torch.full((plan.Q, k), EMPTY_KEY, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_rank_topk(ctypes.byref(plan), qp.data_ptr(), gp.data_ptr(),
+                                           sc["within_all"].data_ptr(), sc["below_all"].data_ptr(),
+                                           sc["thresh"].data_ptr(), k, idx_offset, keys.data_ptr(), _stream()))
+        return keys
+
+    def topk_merge(self, parts: torch.Tensor) -> torch.Tensor:
+        dev = _need_cuda(parts)
+        world, Q, k = parts.shape
+        out = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_topk_merge(parts.data_ptr(), world, Q, k, out.data_ptr(), _stream()))
+        return out
+
+
+def split_keys(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """int64 keys -> (dist int32, index int64); empty slots -> -1."""
+    dev = _need_cuda(keys)
+    dist = torch.empty(keys.shape, dtype=torch.int32, device=dev)
+    idx = torch.empty(keys.shape, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cmh_split_keys(keys.data_ptr(), keys.numel(), dist.data_ptr(), idx.data_ptr(), _stream()))
+    return dist, idx
+
+
+# ---------------------------------------------------------------------------------------------------------
+# single-GPU evaluator
+# ---------------------------------------------------------------------------------------------------------
+@dataclass
+class MapResult:
+    map: torch.Tensor            # 0-dim fp64, device
+    ap: torch.Tensor             # [Q] fp64, device
+    tsum: torch.Tensor           # [Q] int32  R_q  (calc_utils.py:75)
+    total: torch.Tensor          # [Q] int32  min(R_q, k)  (calc_utils.py:81)
+    tindex: Optional[torch.Tensor] = None  # [Q, cap] int32, 0 beyond total  (calc_utils.py:88)
+
+
+class Workspace:
+    """Grow-only device scratch for the one-shot C calls (the library allocates nothing)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_WS = Workspace()
+
+
+def map_k(qp, qlp, gp, glp, nbits: int, ncls: int, k: Optional[int] = None, want_tindex: bool = False,
+          tindex_cap: Optional[int] = None, target_blocks: int = 0) -> MapResult:
+    """calc_map_k on packed inputs, one GPU, via the one-shot C call ``cmh_map_k``."""
+    dev = _need_cuda(qp, qlp, gp, glp)
+    Q, N = qp.shape[0], gp.shape[0]
+    plan = _lib.make_plan(Q, N, nbits, ncls, None, target_blocks)
+    ws = _WS.get(plan.workspace_bytes, dev)
+    out = torch.empty((), dtype=torch.float64, device=dev)
+    ap = torch.empty(Q, dtype=torch.float64, device=dev)
+    tsum = torch.empty(Q, dtype=torch.int32, device=dev)
+    total = torch.empty(Q, dtype=torch.int32, device=dev)
+    tindex = None
+    cap = 0
+    if want_tindex:
+        cap = int(tindex_cap if tindex_cap is not None else (min(k, N) if k else N))
+        cap = max(cap, 1)
+        tindex = torch.zeros((Q, cap), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cmh_map_k(ctypes.byref(plan), qp.data_ptr(), qlp.data_ptr(), gp.data_ptr(), glp.data_ptr(),
+                                   int(k) if k else 0, ws.data_ptr(), ws.numel(), out.data_ptr(), ap.data_ptr(),
+                                   tsum.data_ptr(), total.data_ptr(), _ptr(tindex), cap, _stream()))
+    return MapResult(out, ap, tsum, total, tindex)
+
+
+def topk(qp, gp, nbits: int, k: int, idx_offset: int = 0, target_blocks: int = 0) -> torch.Tensor:
+    """First k entries of the stable Hamming ranking as int64 keys ``(dist << 32) | index`` [Q, k]."""
+    dev = _need_cuda(qp, gp)
+    Q, N = qp.shape[0], gp.shape[0]
+    plan = _lib.make_plan(Q, N, nbits, 0, None, target_blocks)
+    ws = _WS.get(plan.workspace_bytes, dev)
+    keys = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().cmh_topk(ctypes.byref(plan), qp.data_ptr(), gp.data_ptr(), k, idx_offset, ws.data_ptr(),
+                                  ws.numel(), keys.data_ptr(), _stream()))
+    return keys
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sharded evaluator (gallery split by contiguous index range over the ranks of a process group)
+# ---------------------------------------------------------------------------------------------------------
+def shard_bounds(n: int, world: int, align: int = 4) -> List[Tuple[int, int]]:
+    """Contiguous [lo, hi) gallery ranges; shard sizes are multiples of ``align`` (16-byte bulk copies)."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    return [(min(r * per, n), min((r + 1) * per, n)) for r in range(world)]
+
+
+class ShardedEvaluator:
+    """mAP / top-k with the gallery sharded over ``group``; queries (and their labels) are replicated.
+
+    Exchange steps (all ``all_gather_into_tensor``; NCCL over NVLink on GPUs, gloo in the CPU tests):
+      mAP    : per-shard histograms [nchunks, bins, Qpad] int32  ->  scan  ->  per-chunk AP partials fp64
+      top-k  : per-shard partial top-k keys [Q, k] int64 (ONE all-gather) -> merge kernel
+    Every rank ends with the identical result.
+    """
+
+    def __init__(self, group=None, stages=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.stages = stages if stages is not None else CudaStages()
+
+    def _gather(self, t: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def _geometry(self, n_local: int, n_geom: Optional[int], device) -> int:
+        if n_geom is not None:
+            return n_geom
+        t = torch.tensor([n_local], dtype=torch.int64, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def map_k(self, qp, qlp, gp_local, glp_local, nbits: int, ncls: int, k: Optional[int] = None,
+              n_geom: Optional[int] = None, tindex_cap: Optional[int] = None) -> MapResult:
+        st = self.stages
+        Q, n_local = qp.shape[0], gp_local.shape[0]
+        n_geom = self._geometry(n_local, n_geom, qp.device)
+        plan = st.make_plan(Q, n_local, nbits, ncls, n_geom)
+        hist = st.hist(plan, qp, qlp, gp_local, glp_local)
+        hist_all = self._gather(hist)                          # [world, nchunks, bins, Qpad]
+        sc = st.scan(plan, hist_all, self.world, self.rank, k)
+        tindex = None
+        if tindex_cap:
+            tindex = torch.zeros((Q, tindex_cap), dtype=torch.int32, device=qp.device)
+        ap_partial = st.rank_map(plan, qp, qlp, gp_local, glp_local, sc, tindex)
+        ap_all = self._gather(ap_partial)                      # [world, nchunks, Qpad]
+        ap, m = st.map_finish(plan, ap_all, sc["total"])
+        if tindex is not None:                                 # each slot is written by exactly one rank
+            self.dist.all_reduce(tindex, op=self.dist.ReduceOp.SUM, group=self.group)
+        return MapResult(m, ap, sc["tsum"][:Q], sc["total"][:Q], tindex)
+
+    def topk(self, qp, gp_local, nbits: int, k: int, idx_offset: int, n_geom: Optional[int] = None) -> torch.Tensor:
+        """north_star exchange: per-shard partial top-k, ONE all-gather, merge."""
+        st = self.stages
+        Q, n_local = qp.shape[0], gp_local.shape[0]
+        n_geom = self._geometry(n_local, n_geom, qp.device)
+        plan = st.make_plan(Q, n_local, nbits, 0, n_geom)
+        hist = st.hist(plan, qp, None, gp_local, None)
+        sc = st.scan(plan, hist, 1, 0, k, with_rel=False)      # local ranking of this shard
+        keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset)
+        parts = self._gather(keys)                             # [world, Q, k]
+        return st.topk_merge(parts)
