@@ -173,12 +173,18 @@ def run_ours(args, cfg, name):
         qB, _, qL, _ = make_inputs(cfg, 1234)  # queries replicated
     host = [t.pin_memory() for t in (qB, rB, qL, rL)]
     d_qB, d_rB, d_qL, d_rL = (t.to(dev) for t in host)
+    if k is None and args.op == "topk":
+        raise SystemExit("top-k needs a workload with k")
+    if args.op == "topk":
+        host = host[:2]
     h2d = sum(t.numel() * t.element_size() for t in host)
+    pinned_keys = torch.empty((Q, k), dtype=torch.int64).pin_memory() if args.op == "topk" else None
 
     st = R.CudaStages()
     ev = R.ShardedEvaluator(stages=st) if world > 1 else None
     plan = st.make_plan(Q, N, K, C)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    keys_buf = torch.empty((Q, k), dtype=torch.int64, device=dev) if args.op == "topk" else None
 
     def step(events=None):
         """pack + evaluate; returns the fp64 mAP (device).  events: optional list collecting stage boundaries."""
@@ -190,6 +196,21 @@ def run_ours(args, cfg, name):
         mark()
         bad = R.new_bad_counter(dev)
         qp, gp = R.pack_codes(d_qB, bad), R.pack_codes(d_rB, bad)
+        if args.op == "topk":
+            mark()
+            if world > 1:
+                keys = ev.topk(qp, gp, K, k, rank * N, n_geom=N)
+                mark()
+                return keys
+            pl = st.make_plan(Q, N, K, 0)
+            hist = st.hist(pl, qp, None, gp, None)
+            mark()
+            sc = st.scan(pl, hist, 1, 0, k, with_rel=False)
+            mark()
+            keys = st.rank_topk(pl, qp, gp, sc, k, 0, keys=keys_buf)
+            mark()
+            mark()
+            return keys
         qlp, glp = R.pack_labels(d_qL, bad), R.pack_labels(d_rL, bad)
         mark()
         if world > 1:
@@ -207,6 +228,11 @@ def run_ours(args, cfg, name):
         return m
 
     def e2e_step():
+        if args.op == "topk":
+            qp = R.pack_codes(host[0].to(dev, non_blocking=True))
+            gp = R.pack_codes(host[1].to(dev, non_blocking=True))
+            keys = ev.topk(qp, gp, K, k, rank * N, n_geom=N) if world > 1 else R.topk(qp, gp, K, k)
+            return pinned_keys.copy_(keys)
         if world == 1:
             return calc_utils.calc_map_k(host[0], host[1], host[2], host[3], k)
         qp = R.pack_codes(host[0].to(dev, non_blocking=True))
@@ -271,14 +297,15 @@ def run_ours(args, cfg, name):
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": name, "Q": Q, "N_per_gpu": N, "N_total": N * world, "bits": K, "classes": C, "k": k,
                    "step": "pack(+-1 fp32 codes, int64 labels) -> hist -> scan -> rank/AP -> mAP",
-                   "l2": "256 MiB flush write between timed steps", "map": float(out.item()) if out is not None else None},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                   "l2": "256 MiB flush write between timed steps", "op": args.op, "map": float(out.item()) if (out is not None and args.op == "map") else None},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16 if args.op == "map" else Q * k * 8,
                 "ms_per_step": e2e_total_ms / len(e2e_ms)},
         "gpu_launches": args.steps * 10,
         "clocks": clocks.summary(),
     }
     if world == 1:
-        names = ["pack", "hist_kernel", "scan", "rank_map_kernel", "map_finish"]
+        names = (["pack", "hist_kernel", "scan", "rank_map_kernel", "map_finish"] if args.op == "map"
+                 else ["pack", "hist_kernel", "scan", "rank_topk_kernel", "none"])
         stage = {n: v / args.steps for n, v in zip(names, stage_ms)}
         W, LW = plan.W, plan.LW
         # algorithmic bytes of the dominant kernel (rank_map): gallery codes+labels once, query codes+labels,
@@ -286,6 +313,9 @@ def run_ours(args, cfg, name):
         alg = (N * (W + LW) * 4 + Q * (W + LW) * 4 + 2 * plan.within_elems * 4 + 2 * plan.below_elems * 4
                + Q * 4 + plan.ap_elems * 8)
         dom = "rank_map_kernel"
+        if args.op == "topk":  # dominant = pass 1; compulsory bytes: gallery + query codes in, histograms out
+            dom = "hist_kernel"
+            alg = N * W * 4 + Q * W * 4 + plan.Qpad * (K + 1) * 4 * st.make_plan(Q, N, K, 0).nchunks
         achieved = alg / (stage[dom] * 1e-3) / 1e9
         line["roofline"] = {
             "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -313,7 +343,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--op", default=None, choices=["map", "topk"],
+                    help="map = calc_map_k (default for C1-C3); topk = Hamming + per-query top-k (default for C4-*)")
     args = ap.parse_args()
+    if args.op is None:
+        args.op = "topk" if args.workload.startswith("C4") else "map"
     cfg = synth.CONFIGS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg, args.workload)

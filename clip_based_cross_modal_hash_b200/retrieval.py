@@ -180,7 +180,7 @@ class CudaStages:
         return o
 
     def rank_map(self, plan: Plan, qp, qlp, gp, glp, sc: Dict[str, torch.Tensor],
-                 tindex: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 tindex: Optional[torch.Tensor] = None, n_total: Optional[int] = None) -> torch.Tensor:
         dev = _need_cuda(qp, qlp, gp, glp, tindex)
         ap_partial = torch.empty((plan.nchunks, plan.Qpad), dtype=torch.float64, device=dev)
         cap = 0
@@ -192,7 +192,8 @@ class CudaStages:
             check(_lib.lib().cmh_rank_map(ctypes.byref(plan), qp.data_ptr(), qlp.data_ptr(), gp.data_ptr(),
                                           glp.data_ptr(), sc["within_all"].data_ptr(), sc["within_rel"].data_ptr(),
                                           sc["below_all"].data_ptr(), sc["below_rel"].data_ptr(),
-                                          sc["total"].data_ptr(), ap_partial.data_ptr(), _ptr(tindex), cap, _stream()))
+                                          sc["total"].data_ptr(), plan.N if n_total is None else n_total,
+                                          ap_partial.data_ptr(), _ptr(tindex), cap, _stream()))
         return ap_partial
 
     def map_finish(self, plan: Plan, ap_partial_all: torch.Tensor, total: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -351,7 +352,7 @@ class ShardedEvaluator:
         tindex = None
         if tindex_cap:
             tindex = torch.zeros((Q, tindex_cap), dtype=torch.int32, device=qp.device)
-        ap_partial = st.rank_map(plan, qp, qlp, gp_local, glp_local, sc, tindex)
+        ap_partial = st.rank_map(plan, qp, qlp, gp_local, glp_local, sc, tindex, n_total=n_geom * self.world)
         ap_all = self._gather(ap_partial)                      # [world, nchunks, Qpad]
         ap, m = st.map_finish(plan, ap_all, sc["total"])
         if tindex is not None:                                 # each slot is written by exactly one rank

@@ -122,11 +122,14 @@ int cmh_scan(const cmh_plan* plan, const uint32_t* hist_all, int world, int rank
  * ap_partial[c][q] = fp64 sum over this chunk's relevant items j with relevant-rank r_j < total[q] of
  *                    fp32(r_j + 1) / fp32(rank_j + 1)      (the same fp32 quotients the reference forms)
  * tindex (may be NULL): tindex[q*cap + r_j] = rank_j + 1 for r_j < min(total[q], cap)  (int32; the
- * reference's `tindex` at calc_utils.py:88) — entries owned by other ranks are left untouched. */
+ * reference's `tindex` at calc_utils.py:88) — entries owned by other ranks are left untouched.
+ * n_total = gallery items over ALL ranks (= plan->N on one GPU); below 2^24 the kernel keeps its running
+ * ranks in fp32 (exact there), which removes the int->float conversions of the AP terms. */
 int cmh_rank_map(const cmh_plan* plan, const uint32_t* qcodes, const uint32_t* qlabels,
                  const uint32_t* gcodes, const uint32_t* glabels, const uint32_t* within_all,
                  const uint32_t* within_rel, const uint32_t* below_all, const uint32_t* below_rel,
-                 const int32_t* total, double* ap_partial, int32_t* tindex, int64_t cap, void* stream);
+                 const int32_t* total, int64_t n_total, double* ap_partial, int32_t* tindex, int64_t cap,
+                 void* stream);
 
 /* ap[q] = (sum over `nparts` chunk partials [nparts][Qpad], in index order) / total[q];
  * *map_out = (sum_q ap[q]) / Q in fp64, fixed order (calc_utils.py:89-90).  nan if any total is 0,

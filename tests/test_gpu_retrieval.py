@@ -167,7 +167,7 @@ def test_sharded_stages_match_single(name, world):
         sc = st.scan(p, hist_all, world, r, c.k)
         assert np.array_equal(sc["total"][: c.Q].cpu().numpy(), c.totals)
         mine = torch.zeros_like(tindex)
-        parts.append(st.rank_map(p, qp, qlp, gp[lo:hi], glp[lo:hi], sc, mine))
+        parts.append(st.rank_map(p, qp, qlp, gp[lo:hi], glp[lo:hi], sc, mine, n_total=c.N))
         assert not ((tindex != 0) & (mine != 0)).any()  # each slot owned by exactly one shard
         tindex += mine
     tix = tindex.cpu().numpy()
