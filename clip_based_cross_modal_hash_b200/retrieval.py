@@ -329,9 +329,10 @@ class ShardedEvaluator:
         self.stages = stages if stages is not None else CudaStages()
 
     def _gather(self, t: torch.Tensor) -> torch.Tensor:
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        t = t.contiguous()
+        flat = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(flat, t, group=self.group)   # rank-major concatenation along dim 0
+        return flat.view((self.world,) + tuple(t.shape))
 
     def _geometry(self, n_local: int, n_geom: Optional[int], device) -> int:
         if n_geom is not None:

@@ -1,0 +1,71 @@
+"""CPU, world_size 2 and 3 over gloo: the host-side exchange logic of ShardedEvaluator (shard geometry,
+all-gather layouts, AP-partial reduction, top-k merge) with the numpy stage stand-in, against the golden
+vectors of the reference.  The CUDA stages are checked on the GPU by tests/test_gpu_retrieval.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, name, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from clip_based_cross_modal_hash_b200 import retrieval as R
+        from oracle import hamming_oracle as ho
+        from tests._golden import Case
+        from tests._oracle_stages import OracleStages
+
+        c = Case(name)
+        W = (c.K + 31) // 32
+        W = 4 if W == 3 else W
+        LW = (c.C + 31) // 32
+        LW = 4 if LW == 3 else LW
+
+        def pad(a, w):
+            out = np.zeros((a.shape[0], w), dtype=np.uint32)
+            out[:, : min(w, a.shape[1])] = a[:, :w]
+            return torch.from_numpy(out.view(np.int32))
+
+        qp, gp = pad(ho.pack_codes(c.qB.numpy()), W), pad(ho.pack_codes(c.rB.numpy()), W)
+        qlp, glp = pad(ho.pack_labels(c.qL.numpy()), LW), pad(ho.pack_labels(c.rL.numpy()), LW)
+        lo, hi = R.shard_bounds(c.N, world)[rank]
+        ev = R.ShardedEvaluator(stages=OracleStages())
+        cap = max(int(c.totals.max()), 1)
+        res = ev.map_k(qp, qlp, gp[lo:hi], glp[lo:hi], c.K, c.C, c.k, tindex_cap=cap)
+        keys = ev.topk(qp, gp[lo:hi], c.K, 50, lo)
+        torch.save({"map": res.map, "total": res.total, "tsum": res.tsum, "tindex": res.tindex, "keys": keys},
+                   os.path.join(out_dir, "r%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,name", [(2, "tiny16"), (3, "odd48"), (2, "mid64_full")])
+def test_sharded_evaluator_over_gloo(tmp_path, world, name):
+    from tests._golden import Case
+
+    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    c = Case(name)
+    outs = [torch.load(os.path.join(str(tmp_path), "r%d.pt" % r)) for r in range(world)]
+    for o in outs:
+        assert abs(o["map"].item() - float(c.map_stable)) <= 4e-7
+        assert np.array_equal(o["total"].numpy(), c.totals) and np.array_equal(o["tsum"].numpy(), c.tsums)
+        tix = o["tindex"].numpy()
+        for q in range(c.Q):
+            assert np.array_equal(tix[q, : c.totals[q]], c.tindex[q])
+        idx = (o["keys"].numpy().view(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        assert np.array_equal(idx, c.order_head[:, :50])
+        assert torch.equal(o["keys"], outs[0]["keys"]) and o["map"] == outs[0]["map"]  # every rank agrees
