@@ -100,6 +100,7 @@ PROTOTYPES = {
     "cmh_label_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],
     "cmh_cosine_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],
     "cmh_euclid_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],
+    "cmh_gemm_bf16": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _i64, _vp],
 }
 
 _lib: Optional[ctypes.CDLL] = None

@@ -171,6 +171,20 @@ int cmh_label_sim_f32(const float* a, int64_t n, const float* b, int64_t m, int 
 int cmh_cosine_sim_f32(const float* a, int64_t n, const float* b, int64_t m, int d, float* out, void* stream);
 int cmh_euclid_sim_f32(const float* a, int64_t n, const float* b, int64_t m, int d, float* out, void* stream);
 
+/* ---- E: encoder building blocks (models/CLIP/model.py) --------------------------------------------------------
+ * cmh_gemm_bf16: out[M][N] = epilogue(A[M][K] . W[N][K]^T + bias[N]) on tcgen05 tensor cores (bf16 in, fp32
+ * accumulate in TMEM).  A and W are bf16, K contiguous (W is exactly torch.nn.Linear.weight); lda/ldw/ldo/ldr in
+ * elements.  Replaces the fp32 nn.Linear / in_proj / out_proj / c_fc / c_proj GEMMs of
+ * ResidualAttentionBlock (models/CLIP/model.py:167-197) and conv1 (patch embed, :219,235). */
+#define CMH_EPI_BF16 0       /* out bf16 = acc + bias                                   */
+#define CMH_EPI_GELU_BF16 1  /* out bf16 = QuickGELU(acc + bias)   (model.py:162-164)   */
+#define CMH_EPI_RESID_F32 2  /* out fp32 = resid + acc + bias      (residual stream)    */
+#define CMH_EPI_F32 3        /* out fp32 = acc + bias                                   */
+#define CMH_EPI_TANH_F32 4   /* out fp32 = tanh(acc + bias)        (DSPH head)          */
+int cmh_gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, int64_t N, int64_t ldw,
+                  const float* bias, int epilogue, void* out, int64_t ldo, const float* resid, int64_t ldr,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif
