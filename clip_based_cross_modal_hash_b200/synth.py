@@ -44,3 +44,116 @@ def clustered_codes(n: int, nbits: int, seed: int, centers: int = 32, flip: floa
     pick = torch.randint(0, centers, (n,), generator=g)
     noise = (torch.rand(n, nbits, generator=g) < flip).to(torch.int8)
     return ((cen[pick] ^ noise).to(torch.float32)) * 2 - 1
+
+
+# ---- encoder side: seeded weights, images and captions ----------------------------------------
+VIT_B32 = dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768, vision_patch_size=32,
+               context_length=77, vocab_size=49408, transformer_width=512, transformer_heads=8, transformer_layers=12)
+# a 2-layer miniature with the same structure (head dim 64): fast CPU parity cases
+TINY = dict(embed_dim=128, image_resolution=224, vision_layers=2, vision_width=128, vision_patch_size=32,
+            context_length=77, vocab_size=1000, transformer_width=128, transformer_heads=2, transformer_layers=2)
+SOT_ID, EOT_ID = 49406, 49407
+
+
+def _normal(g, shape, std):
+    return torch.randn(shape, generator=g, dtype=torch.float32) * std
+
+
+def clip_state_dict(cfg: dict = VIT_B32, seed: int = 0) -> dict:
+    """A random ``state_dict`` with exactly the keys/shapes of the reference's ``CLIP`` (models/CLIP/model.py:270-340)
+    for a ViT backbone; scales follow ``initialize_parameters`` (:342-371).  LayerNorm gains/biases and the Linear
+    biases are randomised too (the reference initialises them to 1/0) so that parity tests exercise them."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    vw, tw, E = cfg["vision_width"], cfg["transformer_width"], cfg["embed_dim"]
+    P, grid = cfg["vision_patch_size"], cfg["image_resolution"] // cfg["vision_patch_size"]
+
+    def tower(prefix, width, layers):
+        proj_std, attn_std, fc_std = (width ** -0.5) * ((2 * layers) ** -0.5), width ** -0.5, (2 * width) ** -0.5
+        for i in range(layers):
+            p = "%sresblocks.%d." % (prefix, i)
+            sd[p + "attn.in_proj_weight"] = _normal(g, (3 * width, width), attn_std)
+            sd[p + "attn.in_proj_bias"] = _normal(g, (3 * width,), 0.02)
+            sd[p + "attn.out_proj.weight"] = _normal(g, (width, width), proj_std)
+            sd[p + "attn.out_proj.bias"] = _normal(g, (width,), 0.02)
+            sd[p + "ln_1.weight"] = 1 + _normal(g, (width,), 0.05)
+            sd[p + "ln_1.bias"] = _normal(g, (width,), 0.05)
+            sd[p + "mlp.c_fc.weight"] = _normal(g, (4 * width, width), fc_std)
+            sd[p + "mlp.c_fc.bias"] = _normal(g, (4 * width,), 0.02)
+            sd[p + "mlp.c_proj.weight"] = _normal(g, (width, 4 * width), proj_std)
+            sd[p + "mlp.c_proj.bias"] = _normal(g, (width,), 0.02)
+            sd[p + "ln_2.weight"] = 1 + _normal(g, (width,), 0.05)
+            sd[p + "ln_2.bias"] = _normal(g, (width,), 0.05)
+
+    sd["visual.class_embedding"] = _normal(g, (vw,), vw ** -0.5)
+    sd["visual.positional_embedding"] = _normal(g, (grid * grid + 1, vw), vw ** -0.5)
+    sd["visual.proj"] = _normal(g, (vw, E), vw ** -0.5)
+    sd["visual.conv1.weight"] = _normal(g, (vw, 3, P, P), (3 * P * P) ** -0.5)
+    sd["visual.ln_pre.weight"] = 1 + _normal(g, (vw,), 0.05)
+    sd["visual.ln_pre.bias"] = _normal(g, (vw,), 0.05)
+    tower("visual.transformer.", vw, cfg["vision_layers"])
+    sd["visual.ln_post.weight"] = 1 + _normal(g, (vw,), 0.05)
+    sd["visual.ln_post.bias"] = _normal(g, (vw,), 0.05)
+    sd["positional_embedding"] = _normal(g, (cfg["context_length"], tw), 0.01)
+    sd["text_projection"] = _normal(g, (tw, E), tw ** -0.5)
+    sd["logit_scale"] = torch.tensor(2.6593)
+    tower("transformer.", tw, cfg["transformer_layers"])
+    sd["token_embedding.weight"] = _normal(g, (cfg["vocab_size"], tw), 0.02)
+    sd["ln_final.weight"] = 1 + _normal(g, (tw,), 0.05)
+    sd["ln_final.bias"] = _normal(g, (tw,), 0.05)
+    return sd
+
+
+def dsph_head_state_dict(in_dim: int, nbits: int, seed: int = 0) -> dict:
+    """Keys of models/DSPH/hash/hash.py HashLayer (img_hash.fc / txt_hash.fc Linear(in_dim, nbits))."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    for m in ("img", "txt"):
+        sd["%s_hash.fc.weight" % m] = _normal(g, (nbits, in_dim), in_dim ** -0.5)
+        sd["%s_hash.fc.bias" % m] = _normal(g, (nbits,), 0.02)
+    return sd
+
+
+def dcmht_head_state_dict(in_dim: int, nbits: int, seed: int = 0) -> dict:
+    """Keys of models/DCMHT/hash/hash.py HashLayer: per modality an nn.MultiheadAttention, a norm
+    (BatchNorm1d for img, LayerNorm for txt, :58-59) and fc2 Linear(in_dim, 2*nbits)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    for m in ("img", "txt"):
+        p = "%s_hash." % m
+        sd[p + "atten.in_proj_weight"] = _normal(g, (3 * in_dim, in_dim), in_dim ** -0.5)
+        sd[p + "atten.in_proj_bias"] = _normal(g, (3 * in_dim,), 0.02)
+        sd[p + "atten.out_proj.weight"] = _normal(g, (in_dim, in_dim), in_dim ** -0.5)
+        sd[p + "atten.out_proj.bias"] = _normal(g, (in_dim,), 0.02)
+        sd[p + "norm.weight"] = 1 + _normal(g, (in_dim,), 0.05)
+        sd[p + "norm.bias"] = _normal(g, (in_dim,), 0.05)
+        if m == "img":
+            sd[p + "norm.running_mean"] = _normal(g, (in_dim,), 0.1)
+            sd[p + "norm.running_var"] = 1 + 0.2 * torch.rand((in_dim,), generator=g)
+            sd[p + "norm.num_batches_tracked"] = torch.tensor(7)
+        sd[p + "fc2.weight"] = _normal(g, (2 * nbits, in_dim), in_dim ** -0.5)
+        sd[p + "fc2.bias"] = _normal(g, (2 * nbits,), 0.05)
+    return sd
+
+
+def random_images(batch: int, seed: int, resolution: int = 224) -> torch.Tensor:
+    """fp32 NCHW with post-``Normalize`` statistics (dataset/transformer_dataset.py:41-45)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn((batch, 3, resolution, resolution), generator=g, dtype=torch.float32)
+
+
+def random_captions(batch: int, seed: int, max_words: int = 32, vocab: int = 49408):
+    """int64 [B, max_words]: SOT, uniform word ids, EOT at position in [3, max_words-2], zero padding; and the
+    key_padding_mask (text == 0) of dataset/transformer_dataset.py:82-86.  For a reduced vocabulary the SOT/EOT ids
+    are the two largest ids, so that argmax still finds EOT (models/CLIP/model.py:379)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sot, eot = vocab - 2, vocab - 1
+    text = torch.zeros((batch, max_words), dtype=torch.int64)
+    ends = torch.randint(3, max_words - 1, (batch,), generator=g)
+    words = torch.randint(1, sot, (batch, max_words), generator=g)
+    for b in range(batch):
+        e = int(ends[b])
+        text[b, 0] = sot
+        text[b, 1:e] = words[b, 1:e]
+        text[b, e] = eot
+    return text, text == 0
