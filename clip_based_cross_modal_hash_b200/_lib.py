@@ -101,7 +101,16 @@ PROTOTYPES = {
     "cmh_cosine_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],
     "cmh_euclid_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],
     "cmh_gemm_bf16": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _i64, _vp],
+    "cmh_encoder_workspace_bytes": [_vp, _i64, _i32],
+    "cmh_encode_image": [_vp, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp],
+    "cmh_encode_text": [_vp, _vp, _vp, _i64, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp],
+    "cmh_layernorm": [_vp, _i64, _i32, _vp, _vp, ctypes.c_float, _vp, _i32, _vp],
+    "cmh_attention_bf16": [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp],
+    "cmh_linear_f32": [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp],
+    "cmh_head_dsph": [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
+    "cmh_head_dcmht": [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp],
 }
+_RESTYPES = {"cmh_last_error": ctypes.c_char_p, "cmh_encoder_workspace_bytes": ctypes.c_int64}
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -124,7 +133,7 @@ def lib() -> ctypes.CDLL:
         for name, argtypes in PROTOTYPES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_char_p if name == "cmh_last_error" else ctypes.c_int
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
         if handle.cmh_abi_version() != 1:
             raise CmhError("libcmh.so ABI version mismatch")
         _lib = handle

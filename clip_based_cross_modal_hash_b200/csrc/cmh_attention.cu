@@ -1,0 +1,245 @@
+// cmh_attention.cu — multi-head self-attention for the short CLIP sequences (50 image tokens, 32 text tokens).
+//
+// replaces nn.MultiheadAttention(x, x, x, need_weights=True, attn_mask, key_padding_mask) as called from
+// ResidualAttentionBlock.attention (models/CLIP/model.py:181-189) between the in_proj and out_proj GEMMs.
+//
+// One thread block per (sample, head): the whole head (L <= 128 rows of Q, K, V, head dim 64) lives in shared
+// memory, one warp owns 16 query rows.  S = Q.K^T and O = P.V run on the warp-level tensor-core path
+// (mma.sync m16n8k16, bf16 in / fp32 accumulate; tiles of 16 x L x 64 are far below a tcgen05 M=128 atom),
+// softmax stays in fp32 registers, the probabilities never leave the SM — the reference materialises
+// [B.H, L, L] probabilities plus their head average in HBM for every block (need_weights=True) although only the
+// last block's CLS / EOS row is ever read (model.py:265, :381).  That one row is written on request.
+// HBM traffic per layer = read qkv (M x 3D bf16) + write out (M x D bf16): the kernel is HBM-bound.
+#include <cuda_bf16.h>
+
+#include "cmh_common.cuh"
+#include "cmh_encoder.h"
+
+namespace cmh {
+namespace {
+
+constexpr int DH = 64;  // head dimension of every CLIP transformer (width / 64 heads, model.py:300,465)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// byte offset of 16-byte chunk `c` of row `r` in a [rows][64] bf16 tile (128-byte rows, XOR swizzle => conflict-free ldmatrix)
+__device__ __forceinline__ uint32_t tile_off(int r, int c) { return uint32_t(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+struct AttnParams {
+    const __nv_bfloat16* qkv;  // [B*L][3*D]: q | k | v, head h at columns h*64
+    __nv_bfloat16* out;        // [B*L][D]
+    const uint8_t* pad;        // [B][L] key_padding_mask (1 = ignore key) or null
+    float* probs;              // [B][H][L] probabilities of one query row per sample, or null
+    const int32_t* probs_row;  // [B] query row to report (text: EOS), null => row 0 (image: CLS)
+    int L, H, D, causal;
+};
+
+template <int LP>
+__global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
+    constexpr int NT = LP / 8;  // key tiles of 8
+    extern __shared__ __align__(128) uint8_t attn_smem[];
+    uint8_t* sq = attn_smem;
+    uint8_t* sk = sq + LP * 128;
+    uint8_t* sv = sk + LP * 128;
+    uint8_t* spad = sv + LP * 128;
+
+    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int L = p.L, D = p.D;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const __nv_bfloat16* base = p.qkv + size_t(b) * L * 3 * D + h * DH;
+
+    for (int i = tid; i < LP * 8 * 3; i += LP * 2) {
+        const int part = i / (LP * 8), rem = i % (LP * 8), r = rem >> 3, c = rem & 7;
+        uint8_t* dst = (part == 0 ? sq : part == 1 ? sk : sv) + tile_off(r, c);
+        const bool valid = r < L;
+        cp_async16(dst, base + size_t(valid ? r : 0) * 3 * D + part * D + c * 8, valid);
+    }
+    for (int j = tid; j < LP; j += LP * 2) spad[j] = (j >= L) || (p.pad && p.pad[size_t(b) * L + j]);
+    cp_async_wait_all();
+    __syncthreads();
+    if (warp * 16 >= L) return;  // no valid query row in this warp (block-level syncs are all behind us)
+
+    // ---- S = Q K^T -------------------------------------------------------------------------------------
+    float s[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    const uint32_t q_base = smem_u32(sq), k_base = smem_u32(sk), v_base = smem_u32(sv);
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4(q_base + tile_off(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)), a0, a1, a2, a3);
+#pragma unroll
+        for (int n = 0; n < NT; n += 2) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(k_base + tile_off(n * 8 + (lane >> 4) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+            mma_bf16(s[n], a0, a1, a2, a3, b0, b1);
+            mma_bf16(s[n + 1], a0, a1, a2, a3, b2, b3);
+        }
+    }
+
+    // ---- masked softmax over keys (fp32; scale = 1/sqrt(64) folded into the exp2 argument) ---------------
+    const int r0 = warp * 16 + (lane >> 2), r1 = r0 + 8;
+    const float kscale = 0.125f * 1.4426950408889634f;
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int j = n * 8 + (lane & 3) * 2 + e;
+            const bool dead = spad[j];
+            if (dead || (p.causal && j > r0)) s[n][e] = -INFINITY;
+            if (dead || (p.causal && j > r1)) s[n][2 + e] = -INFINITY;
+            m0 = fmaxf(m0, s[n][e]);
+            m1 = fmaxf(m1, s[n][2 + e]);
+        }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            s[n][e] = exp2f((s[n][e] - m0) * kscale);
+            s[n][2 + e] = exp2f((s[n][2 + e] - m1) * kscale);
+            sum0 += s[n][e];
+            sum1 += s[n][2 + e];
+        }
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;  // a fully masked row gives nan, like the reference
+
+    if (p.probs) {  // need_weights row (model.py:265 CLS row, :381 EOS row) for the head average
+        const int want = p.probs_row ? p.probs_row[b] : 0;
+        float* dst = p.probs + (size_t(b) * p.H + h) * L;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = n * 8 + (lane & 3) * 2 + e;
+                if (j < L && r0 == want) dst[j] = s[n][e] * inv0;
+                if (j < L && r1 == want) dst[j] = s[n][2 + e] * inv1;
+            }
+        }
+    }
+
+    // ---- O = P V ------------------------------------------------------------------------------------------
+    float o[DH / 8][4];
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < LP / 16; ++kk) {
+        const uint32_t a0 = pack2(s[2 * kk][0], s[2 * kk][1]), a1 = pack2(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t a2 = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dn = 0; dn < DH / 8; dn += 2) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(v_base + tile_off(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), dn + (lane >> 4)), b0, b1, b2, b3);
+            mma_bf16(o[dn], a0, a1, a2, a3, b0, b1);
+            mma_bf16(o[dn + 1], a0, a1, a2, a3, b2, b3);
+        }
+    }
+
+    // ---- normalise, stage through this warp's own (now dead) Q rows, store 16 bytes per lane --------------
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+        *reinterpret_cast<uint32_t*>(sq + tile_off(r0, n) + (lane & 3) * 4) = pack2(o[n][0] * inv0, o[n][1] * inv0);
+        *reinterpret_cast<uint32_t*>(sq + tile_off(r1, n) + (lane & 3) * 4) = pack2(o[n][2] * inv1, o[n][3] * inv1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + 32 * i, r = warp * 16 + (idx >> 3), c = idx & 7;
+        if (r < L) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sq + tile_off(r, c));
+            *reinterpret_cast<uint4*>(p.out + (size_t(b) * L + r) * D + h * DH + c * 8) = v;
+        }
+    }
+}
+
+// probabilities [B][H][L] -> head average [B][L] with the reported query's own column cleared when asked
+// (model.py:382: attn_weight[arange, EOS] = 0), dropping the first `skip` columns (model.py:265: [:, 0, 1:]).
+__global__ void attn_mean_kernel(const float* __restrict__ probs, const int32_t* __restrict__ zero_col, float* out, int B,
+                                 int H, int L, int skip) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * (L - skip)) return;
+    const int b = i / (L - skip), j = i % (L - skip) + skip;
+    float acc = 0.f;
+    for (int h = 0; h < H; ++h) acc += probs[(size_t(b) * H + h) * L + j];
+    acc /= float(H);
+    if (zero_col && zero_col[b] == j) acc = 0.f;
+    out[i] = acc;
+}
+
+}  // namespace
+
+int attention_bf16(const void* qkv, int64_t B, int L, int H, const uint8_t* pad, int causal, void* out, float* probs,
+                   const int32_t* probs_row, cudaStream_t st) {
+    CMH_REQUIRE(qkv && out && B > 0 && L > 0 && H > 0, "attention: bad arguments");
+    CMH_REQUIRE(L <= 128, "attention: sequence length %d > 128 is not supported", L);
+    CMH_REQUIRE(B * H < (int64_t(1) << 31), "attention: too many (sample, head) pairs");
+    AttnParams p{};
+    p.qkv = static_cast<const __nv_bfloat16*>(qkv), p.out = static_cast<__nv_bfloat16*>(out), p.pad = pad;
+    p.probs = probs, p.probs_row = probs_row, p.L = L, p.H = H, p.D = H * DH, p.causal = causal;
+    const unsigned grid = unsigned(B * H);
+    if (L <= 32) {
+        attn_kernel<32><<<grid, 64, 32 * 385, st>>>(p);
+    } else if (L <= 64) {
+        attn_kernel<64><<<grid, 128, 64 * 385, st>>>(p);
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            CMH_CUDA_TRY(cudaFuncSetAttribute(attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 385));
+            configured = true;
+        }
+        attn_kernel<128><<<grid, 256, 128 * 385, st>>>(p);
+    }
+    CMH_LAUNCH_CHECK("attn_kernel");
+    return CMH_OK;
+}
+
+int attention_mean(const float* probs, int64_t B, int H, int L, int skip, const int32_t* zero_col, float* out,
+                   cudaStream_t st) {
+    const int n = int(B) * (L - skip);
+    attn_mean_kernel<<<(n + 255) / 256, 256, 0, st>>>(probs, zero_col, out, int(B), H, L, skip);
+    CMH_LAUNCH_CHECK("attn_mean_kernel");
+    return CMH_OK;
+}
+
+}  // namespace cmh
+
+extern "C" int cmh_attention_bf16(const void* qkv, int64_t batch, int seq_len, int heads, const uint8_t* key_padding_mask,
+                                  int causal, void* out, void* stream) {
+    return cmh::attention_bf16(qkv, batch, seq_len, heads, key_padding_mask, causal, out, nullptr, nullptr,
+                               cmh::as_stream(stream));
+}

@@ -185,6 +185,95 @@ int cmh_gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* 
                   const float* bias, int epilogue, void* out, int64_t ldo, const float* resid, int64_t ldr,
                   void* stream);
 
+
+/* ---- E: CLIP encoders (models/CLIP/model.py) ---------------------------------------------------------------------
+ * Weights are DEVICE pointers; matrices are bf16 in torch.nn.Linear layout ([out][in], `in` contiguous), vectors
+ * (biases, LayerNorm gain/bias, embeddings) fp32.  The structs below are plain host structs filled by the caller
+ * (the Python shim builds them from a reference `state_dict`; key names in the comments). */
+typedef struct cmh_block_weights {      /* one ResidualAttentionBlock (model.py:167-197), prefix ...resblocks.<i>.  */
+    const float* ln1_gain;  const float* ln1_bias;    /* ln_1.weight / ln_1.bias                                   */
+    const void*  w_qkv;     const float* b_qkv;       /* attn.in_proj_weight [3D][D] / attn.in_proj_bias [3D]      */
+    const void*  w_out;     const float* b_out;       /* attn.out_proj.weight [D][D] / .bias                       */
+    const float* ln2_gain;  const float* ln2_bias;    /* ln_2.*                                                    */
+    const void*  w_fc;      const float* b_fc;        /* mlp.c_fc.weight [4D][D] / .bias                           */
+    const void*  w_proj;    const float* b_proj;      /* mlp.c_proj.weight [D][4D] / .bias                         */
+} cmh_block_weights;
+
+typedef struct cmh_tower {
+    int32_t width, layers, heads, out_dim;            /* heads = width / 64 (model.py:300,465)                     */
+    const cmh_block_weights* blocks;                  /* HOST array [layers]                                       */
+    const float* ln_out_gain; const float* ln_out_bias; /* visual.ln_post.* | ln_final.*                           */
+    const void*  w_out_proj;                          /* bf16 [out_dim][width] = visual.proj^T | text_projection^T */
+    const float* pos_emb;                             /* visual.positional_embedding [grid^2+1][D] | positional_embedding [ctx][D] */
+    /* image tower only (width of the text tower: leave zero/NULL) */
+    int32_t patch, resolution;                        /* 32, 224                                                   */
+    const void*  w_patch;                             /* bf16 [D][3*patch*patch] = visual.conv1.weight flattened   */
+    const float* cls_emb;                             /* visual.class_embedding [D]                                */
+    const float* ln_pre_gain; const float* ln_pre_bias; /* visual.ln_pre.*                                         */
+    /* text tower only */
+    int32_t vocab, context;                           /* 49408, 77                                                 */
+    const float* tok_emb;                             /* token_embedding.weight [vocab][D] fp32                    */
+    int64_t eot_id;                                   /* 49407 (model.py:384)                                      */
+} cmh_tower;
+
+/* Workspace bytes for `batch` samples of `seq_len` tokens (image tower: seq_len = grid^2 + 1). */
+int64_t cmh_encoder_workspace_bytes(const cmh_tower* tower, int64_t batch, int32_t seq_len);
+
+/* CLIP.encode_image (model.py:370 -> VisionTransformer.forward :232-268).
+ * images [B][3][R][R] fp32 NCHW.  Outputs (fp32): cls_out [B][out_dim] (required);
+ * tokens_out [B][L][out_dim] = ln_post + projection of ALL tokens (model.py:257-260; NULL = skip, the plain
+ * encode_image only returns x[0]); attn_out [B][L-1] = last block's head-averaged CLS attention row without the CLS
+ * column (model.py:265; NULL = skip).  The reference's seq_tokens [L-1][B][E] is tokens_out[:,1:].permute(1,0,2). */
+int cmh_encode_image(const cmh_tower* tower, const float* images, int64_t batch, void* workspace, size_t workspace_bytes,
+                     float* cls_out, float* tokens_out, float* attn_out, void* stream);
+
+/* CLIP.encode_text (model.py:373-396).  text [B][L] int64 token ids; key_padding_mask [B][L] uint8 (1 = pad) or NULL.
+ * Outputs: eos_out [B][out_dim] fp32 (required); tokens_out [B][L][out_dim] (NULL = skip);
+ * attn_out [B][L] = last block's head-averaged attention row of the EOS query with its own column zeroed
+ * (model.py:381-382); new_mask_out [B][L] uint8 = key_padding_mask | (text == eot_id) (model.py:384).
+ * L <= 128 and L <= tower->context. */
+int cmh_encode_text(const cmh_tower* tower, const int64_t* text, const uint8_t* key_padding_mask, int64_t batch,
+                    int32_t seq_len, void* workspace, size_t workspace_bytes, float* eos_out, float* tokens_out,
+                    float* attn_out, uint8_t* new_mask_out, void* stream);
+
+/* Building blocks, exported for the per-kernel parity tests:
+ * cmh_layernorm: out[r] = LayerNorm(x[r]) (fp32 statistics, model.py:153-159); out bf16 or fp32.
+ * cmh_attention_bf16: softmax(q.k^T/8 + masks).v per (sample, head); qkv bf16 [B*L][3*heads*64] (q|k|v), out bf16
+ * [B*L][heads*64]; causal = build_attention_mask (model.py:358-364). */
+int cmh_layernorm(const float* x, int64_t rows, int width, const float* gain, const float* bias, float eps, void* out,
+                  int out_f32, void* stream);
+int cmh_attention_bf16(const void* qkv, int64_t batch, int seq_len, int heads, const uint8_t* key_padding_mask, int causal,
+                       void* out, void* stream);
+
+/* ---- H: hash heads (fp32) -----------------------------------------------------------------------------------------
+ * cmh_linear_f32: out[r][n] = act((x[r].W[n] + bias[n]) * scale[n] + shift[n]); W [out_dim][in_dim] fp32; bias, scale,
+ * shift may be NULL (scale and shift together). */
+#define CMH_ACT_NONE 0
+#define CMH_ACT_TANH 1
+#define CMH_ACT_RELU 2
+int cmh_linear_f32(const float* x, int64_t rows, int in_dim, const float* weight, const float* bias, int out_dim,
+                   const float* scale, const float* shift, int act, float* out, int64_t ldo, void* stream);
+
+/* DSPH head, eval mode (models/DSPH/hash/hash.py:6-15): hash [rows][nbits] = tanh(feat.W^T + b);
+ * packed (may be NULL) = bit-packed sign (runners/base.py:407-410: +1 iff hash > 0). */
+int cmh_head_dsph(const float* feat, int64_t rows, int in_dim, const float* weight, const float* bias, int nbits, float* hash,
+                  uint32_t* packed, void* stream);
+
+/* DCMHT head, eval mode (models/DCMHT/hash/hash.py:35-46), one modality. */
+typedef struct cmh_dcmht_head {
+    const float* w_v;   const float* b_v;      /* atten.in_proj_weight[2D:3D] [D][D] / atten.in_proj_bias[2D:3D]       */
+    const float* w_out; const float* b_out;    /* atten.out_proj.*                                                     */
+    const float* bn_scale; const float* bn_shift; /* image: norm.weight/sqrt(running_var+eps), norm.bias - running_mean*scale; text: NULL */
+    const float* norm_gain; const float* norm_bias; /* text: LayerNorm norm.weight / norm.bias; image: NULL            */
+    float eps;                                  /* 1e-5                                                                 */
+    const float* w_fc2; const float* b_fc2;    /* fc2.* [2*nbits][D]                                                   */
+} cmh_dcmht_head;
+/* scratch: fp32 [rows*(2*in_dim + 2*nbits)].  probs [rows][2*nbits] (may be NULL) = pairwise-softmax output of the
+ * head; packed (may be NULL): bit j = 1 iff probs[2j+1] > probs[2j] (DCMHTTrainer.make_hash_code,
+ * runners/DCMHT/runner.py:83-95). */
+int cmh_head_dcmht(const float* feat, int64_t rows, int in_dim, const cmh_dcmht_head* head, int nbits, float* scratch,
+                   float* probs, uint32_t* packed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
