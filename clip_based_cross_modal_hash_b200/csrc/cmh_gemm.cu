@@ -4,13 +4,15 @@
 //
 // replaces the fp32 cuBLAS SGEMMs behind nn.Linear / nn.MultiheadAttention / conv1 of models/CLIP/model.py:167-268.
 //
-// Persistent, warp-specialised, one CTA per SM:
+// Persistent, warp-specialised, one CTA per SM.  CG = 2 pairs the two SMs of a TPC on one 256 x BN tile
+// (tcgen05.mma.cta_group::2): each CTA stages its own 128 rows of A and HALF of the W tile, so the bytes every SM pulls
+// from L2 per MAC drop by ~1.7x — the single-CTA kernel is bound by L2->SM bandwidth (~44 B/clk/SM), not by the tensor pipe.
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) of a 128 x 64 A tile and a BN x 64 W tile
 //                              into a 4..6-stage shared-memory ring, completion on mbarriers (expect_tx)
 //   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x 4
 //                              per stage; tcgen05.commit releases the stage / publishes the accumulator
 //   warp 2      TMEM owner     tcgen05.alloc of 2 x BN fp32 accumulator columns (double buffered) / dealloc
-//   warps 4..7  epilogue       tcgen05.ld 32x32b.x32 -> registers -> bias / QuickGELU / tanh -> swizzled smem staging
+//   warps 4..11 epilogue       tcgen05.ld 32x32b.x32 -> registers -> bias / QuickGELU / tanh -> swizzled smem staging
 //                              -> TMA tile store (cp.async.bulk.tensor) or, for the residual stream, TMA fp32
 //                              reduce-add (cp.reduce.async.bulk.tensor .add) straight into x
 // The epilogue of tile i overlaps the MMAs of tile i+1 through the two TMEM accumulator stages.
@@ -26,19 +28,21 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
-constexpr int SMEM_BUDGET = 192 * 1024;   // operand ring; the epilogue staging takes another 16 KB + 4 KB
-constexpr int STG_WARP_BYTES = 4096;      // per epilogue warp: 2 x (32 rows x 64 B bf16) or 1 x (32 rows x 128 B fp32)
+constexpr int EPI_WARPS = 8;              // two per TMEM lane quarter: they hide each other's TMEM / TMA-store latency
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+constexpr int STG_CHUNK_BYTES = 4096;     // one epilogue chunk: 32 rows x 128 B (64 bf16 or 32 fp32 columns), SWIZZLE_128B
+constexpr int STG_WARP_BYTES = 2 * STG_CHUNK_BYTES;  // double buffered per warp
+constexpr int SMEM_BUDGET = 227 * 1024 - EPI_WARPS * STG_WARP_BYTES - EPI_WARPS * 256 * 4 - 1024 - 256;  // operand ring
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (BN / CG) * BK * 2;  // per CTA: with cta_group::2 each CTA holds half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES < 8 ? SMEM_BUDGET / STAGE_BYTES : 8;
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int SMEM_BYTES = RING_BYTES + 4 * STG_WARP_BYTES + 4 * 256 * 4 /*bias*/ + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = RING_BYTES + EPI_WARPS * STG_WARP_BYTES + EPI_WARPS * 256 * 4 /*bias*/ + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -58,6 +62,32 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// cta_group::2 flavour: executed by both CTAs of the pair; the transaction bytes land on the LEADER's barrier
+// (bit 24 of a shared::cluster address is the CTA rank inside the pair)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(rank)
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -82,25 +112,51 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {  // issued by the same warp of both CTAs of the pair
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
+    if (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    else  // M = 256 over the CTA pair: descriptors address the same offsets in both CTAs' shared memory
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
 }
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+// (CG = 2: on the barrier at this offset in BOTH CTAs of the pair)
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+    if (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                     : "memory");
+    else
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                smem_u32(bar)),
+            "h"(uint16_t(3))
+            : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -126,38 +182,44 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     d |= uint64_t(2) << 61;                  // SWIZZLE_128B
     return d;
 }
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
     return (1u << 4)            // D = fp32
            | (1u << 7)          // A = bf16
            | (1u << 10)         // B = bf16
-           | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+           | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float quick_gelu(float x) {  // x * sigmoid(1.702 x)   models/CLIP/model.py:162-164
-    return x / (1.0f + __expf(-1.702f * x));
+// x * sigmoid(1.702 x)   models/CLIP/model.py:162-164.  MUFU.EX2 + MUFU.RCP (2 ulp; the result is rounded to bf16):
+// an IEEE division here made the epilogue 3x slower than the MMA main loop (one epilogue warp per scheduler, no
+// latency hiding), see profiles/README.md
+__device__ __forceinline__ float quick_gelu(float x) {
+    return __fdividef(x, 1.0f + exp2f(fminf(-1.702f * 1.4426950408889634f * x, 120.f)));  // clamp: __fdividef needs |y| < 2^126
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
-    using C = GemmCfg<BN>;
+    using C = GemmCfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stg_all = smem + C::RING_BYTES;                                   // 4 warps x 4 KB, 1024-aligned
-    float* bias_all = reinterpret_cast<float*>(stg_all + 4 * STG_WARP_BYTES);  // 4 warps x 256 floats
-    uint64_t* full = reinterpret_cast<uint64_t*>(bias_all + 4 * 256);
+    uint8_t* stg_all = smem + C::RING_BYTES;                                           // EPI_WARPS x 8 KB, 1024-aligned
+    float* bias_all = reinterpret_cast<float*>(stg_all + EPI_WARPS * STG_WARP_BYTES);  // EPI_WARPS x 256 floats
+    uint64_t* full = reinterpret_cast<uint64_t*>(bias_all + EPI_WARPS * 256);
     uint64_t* empty = full + C::STAGES;
     uint64_t* tfull = empty + C::STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();  // CTA inside the pair; rank 0 issues the MMAs
+    const int unit = CG == 1 ? int(blockIdx.x) : int(blockIdx.x >> 1);
+    const int units = CG == 1 ? int(gridDim.x) : int(gridDim.x >> 1);
+    const int num_tiles = p.tiles_m * p.tiles_n;  // tiles of (CG*128) x BN
     const int kblocks = int((p.K + BK - 1) / BK);
 
     if (warp == 0 && lane == 0) {
@@ -165,18 +227,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         prefetch_tmap(&tmB);
         prefetch_tmap(&tmO);
         for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&full[s], 1);   // the leader's arrive.expect_tx; bytes come from both CTAs' TMA loads
+            mbar_init(&empty[s], 1);  // tcgen05.commit (multicast to both CTAs when CG = 2)
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 4);  // one arrival per epilogue warp
+            mbar_init(&tempty[s], EPI_WARPS * CG);  // one arrival per epilogue warp of every CTA of the pair
         }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (warp == 2) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
-    __syncthreads();
+    __syncwarp();
+    if (CG == 1) __syncthreads(); else cluster_sync_all();  // the peer's barriers must exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -184,28 +247,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t % p.tiles_m) * BM, n0 = (t / p.tiles_m) * BN;
+            for (int t = unit; t < num_tiles; t += units) {
+                const int m0 = (t % p.tiles_m) * (BM * CG) + int(rank) * BM;
+                const int n0 = (t / p.tiles_m) * BN + int(rank) * (BN / CG);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, kb * BK, m0, &full[stage]);
-                    tma_load_2d(sa + C::A_BYTES, &tmB, kb * BK, n0, &full[stage]);
+                    if (CG == 1) {
+                        mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                        tma_load_2d(sa, &tmA, kb * BK, m0, &full[stage]);
+                        tma_load_2d(sa + C::A_BYTES, &tmB, kb * BK, n0, &full[stage]);
+                    } else {
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+                        tma_load_2d_pair(sa, &tmA, kb * BK, m0, &full[stage]);
+                        tma_load_2d_pair(sa + C::A_BYTES, &tmB, kb * BK, n0, &full[stage]);
+                    }
                     if (++stage == C::STAGES) stage = 0, phase ^= 1u;
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            for (int t = unit; t < num_tiles; t += units, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&tempty[as], aphase ^ 1u);  // epilogue has drained this accumulator stage
+                mbar_wait(&tempty[as], aphase ^ 1u);  // every epilogue warp (of both CTAs) has drained this stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -216,70 +286,81 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advancing 16 bf16 = 32 B inside the swizzle row: +2 in 16-byte units
-                        umma_f16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0);
+                        umma_f16<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+                    umma_commit<CG>(&empty[stage]);  // stage reusable once these MMAs have read it
                     if (++stage == C::STAGES) stage = 0, phase ^= 1u;
                 }
-                umma_commit(&tfull[as]);  // accumulator complete
+                umma_commit<CG>(&tfull[as]);  // accumulator complete
             }
         }
     } else if (warp >= 4) {
-        // Epilogue: each warp owns 32 accumulator rows (its TMEM lane quarter).  A 32-column chunk goes
-        // TMEM -> registers -> (+bias, activation) -> swizzled shared staging -> TMA store (or fp32 reduce-add
-        // into the residual stream), double buffered per warp; stores are asynchronous and fully coalesced.
-        const int e = warp - 4;
+        // Epilogue: warp w reads TMEM lanes 32*(w%4).. (its lane quarter = 32 accumulator rows); the two warps of a
+        // quarter take alternate 128-byte column chunks (64 bf16 / 32 fp32 columns).  A chunk goes TMEM -> registers ->
+        // (+bias, activation) -> swizzled shared staging -> one TMA tile store (or fp32 reduce-add into the residual
+        // stream); staging is double buffered per warp, stores are asynchronous and fully coalesced.
+        const int e = warp - 4, q = warp & 3, half = e >> 2;
         const bool out_bf16 = p.epi == CMH_EPI_BF16 || p.epi == CMH_EPI_GELU_BF16;
+        const int cw = out_bf16 ? 64 : 32;  // columns per chunk
         uint8_t* stg = stg_all + e * STG_WARP_BYTES;
         float* bias_s = bias_all + e * 256;
         int it = 0;
         uint32_t chunk_no = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        for (int t = unit; t < num_tiles; t += units, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int m0 = (t % p.tiles_m) * BM, n0 = (t / p.tiles_m) * BN;
+            const int m0 = (t % p.tiles_m) * (BM * CG) + int(rank) * BM, n0 = (t / p.tiles_m) * BN;
             for (int j = lane; j < BN; j += 32) bias_s[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
             __syncwarp();
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * cw; c0 < BN; c0 += 2 * cw) {
                 if (n0 + c0 >= p.N) break;  // remaining chunks lie outside the matrix (uniform)
-                uint32_t r[32];
-                tmem_ld32(tmem_base + (uint32_t(e * 32) << 16) + uint32_t(as * BN + c0), r);
-                uint8_t* buf = out_bf16 ? stg + (chunk_no & 1u) * (STG_WARP_BYTES / 2) : stg;
+                uint8_t* buf = stg + (chunk_no & 1u) * STG_CHUNK_BYTES;
                 ++chunk_no;
-                if (lane == 0) {  // the store that last used this buffer has finished reading it
-                    if (out_bf16) bulk_wait_read<1>(); else bulk_wait_read<0>();
-                }
+                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + c0);
+                uint8_t* rowp = buf + lane * 128;
+                const int sw = lane & 7;  // SWIZZLE_128B: 16-byte chunk index ^= row & 7
+                uint32_t r[32];
+                tmem_ld32(taddr, r);
+                if (lane == 0) bulk_wait_read<1>();  // the store that last used this buffer has finished reading it
                 __syncwarp();
-                float v[32];
+                if (out_bf16) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + j);
-                    v[j] = __uint_as_float(r[j]) + b.x, v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
-                    v[j + 2] = __uint_as_float(r[j + 2]) + b.z, v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
-                }
-                if (p.epi == CMH_EPI_GELU_BF16) {
+                    for (int hh = 0; hh < 2; ++hh) {
+                        if (hh == 1) tmem_ld32(taddr + 32, r);
+                        float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-                } else if (p.epi == CMH_EPI_TANH_F32) {
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + hh * 32 + j);
+                            v[j] = __uint_as_float(r[j]) + b.x, v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+                            v[j + 2] = __uint_as_float(r[j + 2]) + b.z, v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+                        }
+                        if (p.epi == CMH_EPI_GELU_BF16) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-                }
-                if (out_bf16) {  // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
-                    uint8_t* rowp = buf + lane * 64;
-                    const int sw = (lane >> 1) & 3;
+                            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+                        }
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint4 o;
-                        o.x = pack_bf16(v[8 * c], v[8 * c + 1]), o.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
-                        o.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]), o.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
-                        *reinterpret_cast<uint4*>(rowp + ((c ^ sw) << 4)) = o;
+                        for (int c = 0; c < 4; ++c) {
+                            uint4 o;
+                            o.x = pack_bf16(v[8 * c], v[8 * c + 1]), o.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
+                            o.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]), o.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
+                            *reinterpret_cast<uint4*>(rowp + (((hh * 4 + c) ^ sw) << 4)) = o;
+                        }
                     }
-                } else {  // 32 rows x 128 B, SWIZZLE_128B: chunk index ^= row & 7
-                    uint8_t* rowp = buf + lane * 128;
-                    const int sw = lane & 7;
+                } else {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+                        v[j] = __uint_as_float(r[j]) + b.x, v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+                        v[j + 2] = __uint_as_float(r[j + 2]) + b.z, v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+                    }
+                    if (p.epi == CMH_EPI_TANH_F32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+                    }
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         *reinterpret_cast<float4*>(rowp + ((c ^ sw) << 4)) =
@@ -288,24 +369,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if (p.epi == CMH_EPI_RESID_F32) tma_reduce_add_2d(&tmO, n0 + c0, m0 + e * 32, buf);
-                    else tma_store_2d(&tmO, n0 + c0, m0 + e * 32, buf);
+                    if (p.epi == CMH_EPI_RESID_F32) tma_reduce_add_2d(&tmO, n0 + c0, m0 + q * 32, buf);
+                    else tma_store_2d(&tmO, n0 + c0, m0 + q * 32, buf);
                     bulk_commit();
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (lane == 0) {
+                if (CG == 1) mbar_arrive(&tempty[as]);
+                else mbar_arrive_remote(&tempty[as], 0);  // the leader's MMA thread waits for both CTAs
+            }
         }
         if (lane == 0) bulk_wait_read<0>();
     }
     tc_fence_before();
-    __syncthreads();
+    __syncwarp();
+    if (CG == 1) __syncthreads(); else cluster_sync_all();  // the peer may still be reading this CTA's shared memory / TMEM
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, C::TMEM_COLS);
+        tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
     }
 }
+
+int g_force_bn = 0, g_force_cg = 0;  // test/bench hook (cmh_gemm_force_tile): 0 = automatic
 
 // ---- host side ----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -326,16 +413,16 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// output tile map: 32 rows x 32 columns per store, bf16 (64-byte rows, SWIZZLE_64B) or fp32 (128-byte rows, SWIZZLE_128B)
+// output tile map: 32 rows x 128 bytes per store (64 bf16 or 32 fp32 columns), SWIZZLE_128B
 int make_out_tmap(CUtensorMap* map, void* base, int64_t rows, int64_t cols, int64_t ld, bool bf16) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(CMH_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
     cuuint64_t strides[1] = {cuuint64_t(ld) * (bf16 ? 2 : 4)};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {cuuint32_t(bf16 ? 64 : 32), 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CMH_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with CUresult %d", int(r));
     return CMH_OK;
@@ -356,36 +443,46 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
     return CMH_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GemmParams p, cudaStream_t st) {
-    using C = GemmCfg<BN>;
+    using C = GemmCfg<BN, CG>;
     static bool configured = false;
     if (!configured) {
-        CMH_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        CMH_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    p.tiles_m = int(ceil_div(p.M, BM));
+    p.tiles_m = int(ceil_div(p.M, BM * CG));
     p.tiles_n = int(ceil_div(p.N, BN));
     const int tiles = p.tiles_m * p.tiles_n;
-    const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
-    gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, to, p);
-    CMH_LAUNCH_CHECK("gemm_bf16_kernel");
+    const int units = sm_count_cached() / CG;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned((tiles < units ? tiles : units) * CG));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    CMH_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG>, ta, tb, to, p));
     return CMH_OK;
 }
 
-// tile width: fewest "wave x tile cost" units on this device
-int pick_bn(int64_t M, int64_t N) {
+// Tile shape: fewest "waves x bytes one SM pulls from L2 per k-block" units.  The kernels are bound by L2->SM
+// bandwidth before the tensor pipe (profiles/README.md), so a tile costs (128 + BN/CG) rows of 128 bytes per k-block.
+void pick_tile(int64_t M, int64_t N, int* bn_out, int* cg_out) {
     const int sms = sm_count_cached();
-    const int64_t tm = ceil_div(M, BM);
-    int best = 128;
     double best_cost = 1e30;
-    for (int bn : {256, 192, 128}) {
-        if (N < bn && bn != 128) continue;
-        const int64_t tiles = tm * ceil_div(N, bn);
-        const double cost = double(ceil_div(tiles, sms)) * bn;
-        if (cost < best_cost - 1e-9) best_cost = cost, best = bn;
+    *bn_out = 128, *cg_out = 1;
+    for (int cg : {2, 1}) {
+        if (cg == 2 && M <= BM) continue;  // a pair would leave the second CTA without rows
+        for (int bn : {256, 192, 128}) {
+            if (N < bn && bn != 128) continue;
+            const int64_t tiles = ceil_div(M, BM * cg) * ceil_div(N, bn);
+            const double cost = double(ceil_div(tiles, sms / cg)) * (128 + bn / cg);
+            if (cost < best_cost - 1e-9) best_cost = cost, *bn_out = bn, *cg_out = cg;
+        }
     }
-    return best;
 }
 
 }  // namespace
@@ -401,21 +498,38 @@ int gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, i
     CMH_REQUIRE(ldo % (out_bf16 ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: output must be 16-byte aligned per row");
     CMH_REQUIRE(epi != CMH_EPI_RESID_F32 || (resid == out && ldr == ldo),
                 "gemm: the residual epilogue works in place (resid == out): it is a TMA fp32 reduce-add into the stream");
-    const int bn = pick_bn(M, N);
+    int bn = 128, cg = 1;
+    pick_tile(M, N, &bn, &cg);
+    if (g_force_bn > 0) bn = g_force_bn;
+    if (g_force_cg > 0) cg = g_force_cg;
     CUtensorMap ta, tb, to;
     if (int rc = make_tmap(&ta, A, M, K, lda, BM)) return rc;
-    if (int rc = make_tmap(&tb, W, N, K, ldw, bn)) return rc;
+    if (int rc = make_tmap(&tb, W, N, K, ldw, bn / cg)) return rc;
     if (int rc = make_out_tmap(&to, out, M, N, ldo, out_bf16)) return rc;
     GemmParams p{};
     p.M = M, p.N = N, p.K = K, p.bias = bias, p.out = out, p.ldo = ldo, p.resid = resid, p.ldr = ldr, p.epi = epi;
+    if (cg == 2) {
+        switch (bn) {
+            case 256: return launch_gemm<256, 2>(ta, tb, to, p, st);
+            case 192: return launch_gemm<192, 2>(ta, tb, to, p, st);
+            default: return launch_gemm<128, 2>(ta, tb, to, p, st);
+        }
+    }
     switch (bn) {
-        case 256: return launch_gemm<256>(ta, tb, to, p, st);
-        case 192: return launch_gemm<192>(ta, tb, to, p, st);
-        default: return launch_gemm<128>(ta, tb, to, p, st);
+        case 256: return launch_gemm<256, 1>(ta, tb, to, p, st);
+        case 192: return launch_gemm<192, 1>(ta, tb, to, p, st);
+        default: return launch_gemm<128, 1>(ta, tb, to, p, st);
     }
 }
 
 }  // namespace cmh
+
+extern "C" int cmh_gemm_force_tile(int bn, int cta_group) {
+    if (!(bn == 0 || bn == 128 || bn == 192 || bn == 256) || cta_group < 0 || cta_group > 2)
+        return cmh::fail(CMH_ERR_INVALID, "gemm_force_tile: bn in {0,128,192,256}, cta_group in {0,1,2}");
+    cmh::g_force_bn = bn, cmh::g_force_cg = cta_group;
+    return CMH_OK;
+}
 
 extern "C" int cmh_gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, int64_t N, int64_t ldw,
                              const float* bias, int epilogue, void* out, int64_t ldo, const float* resid, int64_t ldr,

@@ -184,6 +184,9 @@ int cmh_euclid_sim_f32(const float* a, int64_t n, const float* b, int64_t m, int
 int cmh_gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, int64_t N, int64_t ldw,
                   const float* bias, int epilogue, void* out, int64_t ldo, const float* resid, int64_t ldr,
                   void* stream);
+/* Test / tuning hook: pin the tile width (128, 192, 256; 0 = automatic) and the CTA group (1 = one SM per tile,
+ * 2 = tcgen05 cta_group::2 pairs on 256-row tiles; 0 = automatic) of every following cmh_gemm_bf16 call. */
+int cmh_gemm_force_tile(int bn, int cta_group);
 
 
 /* ---- E: CLIP encoders (models/CLIP/model.py) ---------------------------------------------------------------------

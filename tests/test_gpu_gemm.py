@@ -67,6 +67,30 @@ def test_gemm_matches_fp32_reference(M, N, K, epi):
     if epi == EPI_F32:
         got = run_gemm(a, w, None, epi)
         assert bool(((got - reference(a, w, None, epi)).abs() <= 2e-5 * mass + 1e-6).all())
+@pytest.mark.parametrize("bn,cg", [(128, 1), (192, 1), (256, 1), (128, 2), (192, 2), (256, 2)])
+@pytest.mark.parametrize("M,N,K,epi", [(12800, 2304, 768, EPI_BF16), (12800, 768, 3072, EPI_RESID_F32), (8192, 2048, 512, EPI_GELU_BF16),
+                                       (300, 136, 192, EPI_F32), (1, 16, 64, EPI_F32), (257, 520, 320, EPI_BF16), (129, 768, 128, EPI_RESID_F32)])
+def test_gemm_every_tile_configuration(bn, cg, M, N, K, epi):
+    """Each (tile width, CTA group) kernel instance, pinned through cmh_gemm_force_tile, including ragged edges where the
+    second CTA of a pair has few or no rows / columns."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + bn + cg)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * (K ** -0.5)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) if epi == EPI_RESID_F32 else None
+    _lib.check(_lib.lib().cmh_gemm_force_tile(bn, cg))
+    try:
+        got = run_gemm(a, w, bias, epi, resid).float()
+    finally:
+        _lib.check(_lib.lib().cmh_gemm_force_tile(0, 0))
+    want = reference(a, w, bias, epi, resid)
+    mass = a.float().abs() @ w.float().abs().t() + 1.0
+    tol = 2e-5 * mass + (2.0 ** -8) * want.abs() * (1 if epi in (EPI_BF16, EPI_GELU_BF16) else 0) + 1e-6
+    if epi == EPI_GELU_BF16:
+        tol = tol + 2e-6 * want.abs() + 1e-6   # MUFU.EX2/RCP sigmoid: 2 ulp before the bf16 rounding
+    assert bool(((got - want).abs() <= tol).all()), float(((got - want).abs() / tol).max())
+
+
 def test_gemm_repeated_launches_are_deterministic():
     g = torch.Generator(device="cuda").manual_seed(5)
     a = torch.randn(4096, 768, device="cuda", generator=g).to(torch.bfloat16)
