@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const __nv_bfloat16* base = p.qkv + size_t(b) * L * 3 * D + h * DH;
 
+    pdl_wait();
     for (int i = tid; i < LP * 8 * 3; i += LP * 2) {
         const int part = i / (LP * 8), rem = i % (LP * 8), r = rem >> 3, c = rem & 7;
         uint8_t* dst = (part == 0 ? sq : part == 1 ? sk : sv) + tile_off(r, c);
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
     for (int j = tid; j < LP; j += LP * 2) spad[j] = (j >= L) || (p.pad && p.pad[size_t(b) * L + j]);
     cp_async_wait_all();
     __syncthreads();
+    pdl_launch_dependents();
     if (warp * 16 >= L) return;  // no valid query row in this warp (block-level syncs are all behind us)
 
     // ---- S = Q K^T -------------------------------------------------------------------------------------
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
 __global__ void attn_mean_kernel(const float* __restrict__ probs, const int32_t* __restrict__ zero_col, float* out, int B,
                                  int H, int L, int skip) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
     if (i >= B * (L - skip)) return;
     const int b = i / (L - skip), j = i % (L - skip) + skip;
     float acc = 0.f;
@@ -213,26 +216,24 @@ int attention_bf16(const void* qkv, int64_t B, int L, int H, const uint8_t* pad,
     p.probs = probs, p.probs_row = probs_row, p.L = L, p.H = H, p.D = H * DH, p.causal = causal;
     const unsigned grid = unsigned(B * H);
     if (L <= 32) {
-        attn_kernel<32><<<grid, 64, 32 * 385, st>>>(p);
+        CMH_CUDA_TRY(launch_kernel(attn_kernel<32>, dim3(grid), dim3(64), 32 * 385, st, 1, p));
     } else if (L <= 64) {
-        attn_kernel<64><<<grid, 128, 64 * 385, st>>>(p);
+        CMH_CUDA_TRY(launch_kernel(attn_kernel<64>, dim3(grid), dim3(128), 64 * 385, st, 1, p));
     } else {
         static bool configured = false;
         if (!configured) {
             CMH_CUDA_TRY(cudaFuncSetAttribute(attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 385));
             configured = true;
         }
-        attn_kernel<128><<<grid, 256, 128 * 385, st>>>(p);
+        CMH_CUDA_TRY(launch_kernel(attn_kernel<128>, dim3(grid), dim3(256), 128 * 385, st, 1, p));
     }
-    CMH_LAUNCH_CHECK("attn_kernel");
     return CMH_OK;
 }
 
 int attention_mean(const float* probs, int64_t B, int H, int L, int skip, const int32_t* zero_col, float* out,
                    cudaStream_t st) {
     const int n = int(B) * (L - skip);
-    attn_mean_kernel<<<(n + 255) / 256, 256, 0, st>>>(probs, zero_col, out, int(B), H, L, skip);
-    CMH_LAUNCH_CHECK("attn_mean_kernel");
+    CMH_CUDA_TRY(launch_kernel(attn_mean_kernel, dim3((n + 255) / 256), dim3(256), 0, st, 1, probs, zero_col, out, int(B), H, L, skip));
     return CMH_OK;
 }
 

@@ -38,6 +38,37 @@ static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// Every encoder kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may become resident
+// while its predecessor in the stream is still draining.  pdl_wait() blocks until the predecessor has completed and
+// its memory is visible (no-op for a normal launch); everything before it (barrier init, TMEM allocation, tensor-map
+// prefetch) overlaps the predecessor's tail.  pdl_launch_dependents() lets the successor start launching.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();  // cmh_core.cu; CMH_NO_PDL=1 in the environment disables the launch attribute
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                          Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = unsigned(cluster), attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = attr, cfg.numAttrs = unsigned(n);
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- shared-memory barrier + bulk async copy (TMA 1-D) -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

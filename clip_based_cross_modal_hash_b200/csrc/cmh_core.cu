@@ -1,6 +1,7 @@
 // cmh_core.cu — error reporting and device queries of libcmh.so.
 #include "cmh_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace cmh {
@@ -14,6 +15,14 @@ int fail(int code, const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("CMH_NO_PDL");
+        return !(e && e[0] && e[0] != '0');
+    }();
+    return on;
 }
 
 int sm_count_cached() {

@@ -7,12 +7,12 @@
 // Persistent, warp-specialised, one CTA per SM.  CG = 2 pairs the two SMs of a TPC on one 256 x BN tile
 // (tcgen05.mma.cta_group::2): each CTA stages its own 128 rows of A and HALF of the W tile, so the bytes every SM pulls
 // from L2 per MAC drop by ~1.7x — the single-CTA kernel is bound by L2->SM bandwidth (~44 B/clk/SM), not by the tensor pipe.
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) of a 128 x 64 A tile and a BN x 64 W tile
+//   warp 8      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) of a 128 x 64 A tile and a BN x 64 W tile
 //                              into a 4..6-stage shared-memory ring, completion on mbarriers (expect_tx)
-//   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x 4
+//   warp 9      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x 4
 //                              per stage; tcgen05.commit releases the stage / publishes the accumulator
-//   warp 2      TMEM owner     tcgen05.alloc of 2 x BN fp32 accumulator columns (double buffered) / dealloc
-//   warps 4..11 epilogue       tcgen05.ld 32x32b.x32 -> registers -> bias / QuickGELU / tanh -> swizzled smem staging
+//   warp 10     TMEM owner     tcgen05.alloc of 2 x BN fp32 accumulator columns (double buffered) / dealloc
+//   warps 0..7  epilogue       tcgen05.ld 32x32b.x32 -> registers -> bias / QuickGELU / tanh -> swizzled smem staging
 //                              -> TMA tile store (cp.async.bulk.tensor) or, for the residual stream, TMA fp32
 //                              reduce-add (cp.reduce.async.bulk.tensor .add) straight into x
 // The epilogue of tile i overlaps the MMAs of tile i+1 through the two TMEM accumulator stages.
@@ -29,7 +29,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;              // two per TMEM lane quarter: they hide each other's TMEM / TMA-store latency
-constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1, TMEM_WARP = EPI_WARPS + 2;
+// The latency-critical single-thread roles get the HIGHEST warp ids: the SM's warp arbiter prefers higher ids, and with
+// the epilogue warps above them the MMA issue loop lost ~20 % once an epilogue ran concurrently (profiles/README.md).
+constexpr int GEMM_THREADS = (EPI_WARPS + 3) * 32;
 constexpr int STG_CHUNK_BYTES = 4096;     // one epilogue chunk: 32 rows x 128 B (64 bf16 or 32 fp32 columns), SWIZZLE_128B
 constexpr int STG_WARP_BYTES = 2 * STG_CHUNK_BYTES;  // double buffered per warp
 constexpr int SMEM_BUDGET = 227 * 1024 - EPI_WARPS * STG_WARP_BYTES - EPI_WARPS * 256 * 4 - 1024 - 256;  // operand ring
@@ -54,7 +57,13 @@ struct GemmParams {
     int64_t ldr;
     int epi;
     int tiles_m, tiles_n;
+    long long* trace;  // debug timeline (cmh_gemm_set_trace): [cta][64] SM clock stamps, or null
 };
+
+#define CMH_TRACE(slot)                                                        \
+    do {                                                                       \
+        if (p.trace && (slot) < 64) p.trace[size_t(blockIdx.x) * 64 + (slot)] = clock64(); \
+    } while (0)
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -81,29 +90,52 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default (.release.cta) semantics:
+// the accumulator hand-over is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, not by generic memory;
+// a .release.cluster arrive compiled to MEMBAR.ALL.CTA + ERRBAR and cost ~1/3 of the epilogue (profiles/README.md)
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
         "r"(rank)
         : "memory");
+}
+// One lane of a converged warp.  The single-thread roles run with the WHOLE warp converged and predicate only the
+// tcgen05 / TMA instruction on this: inside an `if (lane == 0)` region the compiler cannot prove the operands uniform
+// and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~145 clk per MMA, issue-bound; profiles/README.md).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 // shared -> global tile store / fp32 reduce-add through the tensor map (clips rows/columns outside the tensor)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* smem_src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_src),
+                 "r"(c0), "r"(c1)
                  : "memory");
 }
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int c0, int c1, const void* smem_src) {
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int c0, int c1, uint32_t smem_src) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 "r"(smem_src), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -189,11 +221,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
            | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 
-// x * sigmoid(1.702 x)   models/CLIP/model.py:162-164.  MUFU.EX2 + MUFU.RCP (2 ulp; the result is rounded to bf16):
-// an IEEE division here made the epilogue 3x slower than the MMA main loop (one epilogue warp per scheduler, no
-// latency hiding), see profiles/README.md
+// x * sigmoid(1.702 x)   models/CLIP/model.py:162-164, as 0.5x + 0.5x * tanh(0.851 x): ONE MUFU op per element
+// (tanh.approx.f32, relative error 2^-11 on the tanh => absolute error <= 2.5e-4 |x|, below the bf16 rounding of the
+// result).  The epilogue owns 128 x 256 elements per tile and the SM has 16 MUFU lanes: an exp2 + reciprocal sigmoid
+// (2 MUFU) alone costs 4096 clk of the 6144 clk a tile's MMAs take, and an IEEE division made the epilogue 3x slower
+// than the main loop (profiles/README.md).
 __device__ __forceinline__ float quick_gelu(float x) {
-    return __fdividef(x, 1.0f + exp2f(fminf(-1.702f * 1.4426950408889634f * x, 120.f)));  // clamp: __fdividef needs |y| < 2^126
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    const float h = 0.5f * x;
+    return fmaf(h, t, h);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -217,12 +254,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();  // CTA inside the pair; rank 0 issues the MMAs
+    if (threadIdx.x == MMA_WARP * 32) CMH_TRACE(0);
     const int unit = CG == 1 ? int(blockIdx.x) : int(blockIdx.x >> 1);
     const int units = CG == 1 ? int(gridDim.x) : int(gridDim.x >> 1);
     const int num_tiles = p.tiles_m * p.tiles_n;  // tiles of (CG*128) x BN
     const int kblocks = int((p.K + BK - 1) / BK);
 
-    if (warp == 0 && lane == 0) {
+    if (warp == PRODUCER_WARP && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         prefetch_tmap(&tmO);
@@ -236,22 +274,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
+    if (warp == TMEM_WARP) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
     __syncwarp();
     if (CG == 1) __syncthreads(); else cluster_sync_all();  // the peer's barriers must exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == MMA_WARP * 32) CMH_TRACE(1);
+    pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are visible from here
+    pdl_launch_dependents();  // the next kernel's blocks may take SMs as this grid's CTAs retire
 
-    if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = unit; t < num_tiles; t += units) {
-                const int m0 = (t % p.tiles_m) * (BM * CG) + int(rank) * BM;
-                const int n0 = (t / p.tiles_m) * BN + int(rank) * (BN / CG);
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1u);
+    if (warp == PRODUCER_WARP) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = unit; t < num_tiles; t += units) {
+            const int m0 = (t % p.tiles_m) * (BM * CG) + int(rank) * BM;
+            const int n0 = (t / p.tiles_m) * BN + int(rank) * (BN / CG);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                if (elect_one()) {
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     if (CG == 1) {
                         mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
@@ -262,12 +303,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tma_load_2d_pair(sa, &tmA, kb * BK, m0, &full[stage]);
                         tma_load_2d_pair(sa + C::A_BYTES, &tmB, kb * BK, n0, &full[stage]);
                     }
-                    if (++stage == C::STAGES) stage = 0, phase ^= 1u;
                 }
+                __syncwarp();
+                if (++stage == C::STAGES) stage = 0, phase ^= 1u;
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+    } else if (warp == MMA_WARP) {
+        if (rank == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -275,52 +317,61 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int t = unit; t < num_tiles; t += units, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
+                if (lane == 0) CMH_TRACE(2 + it * 4);
                 mbar_wait(&tempty[as], aphase ^ 1u);  // every epilogue warp (of both CTAs) has drained this stage
                 tc_fence_after();
+                if (lane == 0) CMH_TRACE(3 + it * 4);
                 const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+                    if (kb == 0 && lane == 0) CMH_TRACE(4 + it * 4);
                     const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
                     const uint64_t adesc = make_desc_sw128(sa), bdesc = make_desc_sw128(sa + C::A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advancing 16 bf16 = 32 B inside the swizzle row: +2 in 16-byte units
-                        umma_f16<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advancing 16 bf16 = 32 B inside the swizzle row: +2 in 16-byte units
+                            umma_f16<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0);
+                        }
+                        umma_commit<CG>(&empty[stage]);  // stage reusable once these MMAs have read it
                     }
-                    umma_commit<CG>(&empty[stage]);  // stage reusable once these MMAs have read it
+                    __syncwarp();
                     if (++stage == C::STAGES) stage = 0, phase ^= 1u;
                 }
-                umma_commit<CG>(&tfull[as]);  // accumulator complete
+                if (elect_one()) umma_commit<CG>(&tfull[as]);  // accumulator complete
+                __syncwarp();
+                if (lane == 0) CMH_TRACE(5 + it * 4);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < EPI_WARPS) {
         // Epilogue: warp w reads TMEM lanes 32*(w%4).. (its lane quarter = 32 accumulator rows); the two warps of a
         // quarter take alternate 128-byte column chunks (64 bf16 / 32 fp32 columns).  A chunk goes TMEM -> registers ->
         // (+bias, activation) -> swizzled shared staging -> one TMA tile store (or fp32 reduce-add into the residual
         // stream); staging is double buffered per warp, stores are asynchronous and fully coalesced.
-        const int e = warp - 4, q = warp & 3, half = e >> 2;
+        const int e = warp, q = warp & 3, half = e >> 2;
         const bool out_bf16 = p.epi == CMH_EPI_BF16 || p.epi == CMH_EPI_GELU_BF16;
         const int cw = out_bf16 ? 64 : 32;  // columns per chunk
-        uint8_t* stg = stg_all + e * STG_WARP_BYTES;
-        float* bias_s = bias_all + e * 256;
+        const uint32_t stg = smem_u32(stg_all + e * STG_WARP_BYTES);
+        const uint32_t bias_s = smem_u32(bias_all + e * 256);
         int it = 0;
         uint32_t chunk_no = 0;
         for (int t = unit; t < num_tiles; t += units, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (t % p.tiles_m) * (BM * CG) + int(rank) * BM, n0 = (t / p.tiles_m) * BN;
-            for (int j = lane; j < BN; j += 32) bias_s[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+            for (int j = lane; j < BN; j += 32) sts32f(bias_s + j * 4, (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f);
             __syncwarp();
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
+            if (e == 0 && lane == 0) CMH_TRACE(34 + it * 2);
 #pragma unroll 1
             for (int c0 = half * cw; c0 < BN; c0 += 2 * cw) {
                 if (n0 + c0 >= p.N) break;  // remaining chunks lie outside the matrix (uniform)
-                uint8_t* buf = stg + (chunk_no & 1u) * STG_CHUNK_BYTES;
+                const uint32_t buf = stg + (chunk_no & 1u) * STG_CHUNK_BYTES;
                 ++chunk_no;
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + c0);
-                uint8_t* rowp = buf + lane * 128;
+                const uint32_t rowp = buf + lane * 128;
                 const int sw = lane & 7;  // SWIZZLE_128B: 16-byte chunk index ^= row & 7
                 uint32_t r[32];
                 tmem_ld32(taddr, r);
@@ -333,7 +384,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + hh * 32 + j);
+                            const float4 b = lds128f(bias_s + (c0 + hh * 32 + j) * 4);
                             v[j] = __uint_as_float(r[j]) + b.x, v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
                             v[j + 2] = __uint_as_float(r[j + 2]) + b.z, v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
                         }
@@ -346,14 +397,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             uint4 o;
                             o.x = pack_bf16(v[8 * c], v[8 * c + 1]), o.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
                             o.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]), o.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
-                            *reinterpret_cast<uint4*>(rowp + (((hh * 4 + c) ^ sw) << 4)) = o;
+                            sts128(rowp + (((hh * 4 + c) ^ sw) << 4), o.x, o.y, o.z, o.w);
                         }
                     }
                 } else {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+                        const float4 b = lds128f(bias_s + (c0 + j) * 4);
                         v[j] = __uint_as_float(r[j]) + b.x, v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
                         v[j + 2] = __uint_as_float(r[j + 2]) + b.z, v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
                     }
@@ -363,8 +414,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
-                        *reinterpret_cast<float4*>(rowp + ((c ^ sw) << 4)) =
-                            make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                        sts128(rowp + ((c ^ sw) << 4), __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                               __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
                 }
                 fence_async_smem();
                 __syncwarp();
@@ -379,6 +430,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) {
                 if (CG == 1) mbar_arrive(&tempty[as]);
                 else mbar_arrive_remote(&tempty[as], 0);  // the leader's MMA thread waits for both CTAs
+                if (e == 0) CMH_TRACE(35 + it * 2);
             }
         }
         if (lane == 0) bulk_wait_read<0>();
@@ -386,13 +438,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_before();
     __syncwarp();
     if (CG == 1) __syncthreads(); else cluster_sync_all();  // the peer may still be reading this CTA's shared memory / TMEM
-    if (warp == 2) {
+    if (warp == TMEM_WARP) {
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
     }
+    if (threadIdx.x == MMA_WARP * 32) CMH_TRACE(63);
 }
 
-int g_force_bn = 0, g_force_cg = 0;  // test/bench hook (cmh_gemm_force_tile): 0 = automatic
+long long* g_trace = nullptr;
+int g_force_bn = 0, g_force_cg = 0, g_force_units = 0;  // test/bench hook (cmh_gemm_force_tile): 0 = automatic
 
 // ---- host side ----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -454,17 +508,10 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     p.tiles_m = int(ceil_div(p.M, BM * CG));
     p.tiles_n = int(ceil_div(p.N, BN));
     const int tiles = p.tiles_m * p.tiles_n;
-    const int units = sm_count_cached() / CG;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(unsigned((tiles < units ? tiles : units) * CG));
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    CMH_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, CG>, ta, tb, to, p));
+    int units = sm_count_cached() / CG;
+    if (g_force_units > 0 && g_force_units < units) units = g_force_units;
+    CMH_CUDA_TRY(launch_kernel(gemm_bf16_kernel<BN, CG>, dim3(unsigned((tiles < units ? tiles : units) * CG)), dim3(GEMM_THREADS),
+                               C::SMEM_BYTES, st, CG, ta, tb, to, p));
     return CMH_OK;
 }
 
@@ -508,6 +555,7 @@ int gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, i
     if (int rc = make_out_tmap(&to, out, M, N, ldo, out_bf16)) return rc;
     GemmParams p{};
     p.M = M, p.N = N, p.K = K, p.bias = bias, p.out = out, p.ldo = ldo, p.resid = resid, p.ldr = ldr, p.epi = epi;
+    p.trace = g_trace;
     if (cg == 2) {
         switch (bn) {
             case 256: return launch_gemm<256, 2>(ta, tb, to, p, st);
@@ -524,10 +572,20 @@ int gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, i
 
 }  // namespace cmh
 
+extern "C" int cmh_gemm_set_trace(long long* device_buffer) {  // [grid][64] clock stamps per CTA; NULL = off
+    cmh::g_trace = device_buffer;
+    return CMH_OK;
+}
+
 extern "C" int cmh_gemm_force_tile(int bn, int cta_group) {
     if (!(bn == 0 || bn == 128 || bn == 192 || bn == 256) || cta_group < 0 || cta_group > 2)
         return cmh::fail(CMH_ERR_INVALID, "gemm_force_tile: bn in {0,128,192,256}, cta_group in {0,1,2}");
     cmh::g_force_bn = bn, cmh::g_force_cg = cta_group;
+    return CMH_OK;
+}
+
+extern "C" int cmh_gemm_force_units(int units) {  // debug: cap the number of CTAs (CG=1) / CTA pairs (CG=2); 0 = all SMs
+    cmh::g_force_units = units;
     return CMH_OK;
 }
 

@@ -67,12 +67,14 @@ layernorm_kernel(const float* __restrict__ x, int64_t rows, int64_t row_mul, con
                  const float* __restrict__ g, const float* __restrict__ b, float eps, void* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t r = int64_t(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+    pdl_wait();
     if (r >= rows) return;
     const int64_t src = r * row_mul + (row_idx ? row_idx[r] : 0);
     const float4* xr = reinterpret_cast<const float4*>(x) + src * (NV * 32);
     float4 v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = xr[i * 32 + lane];
+    pdl_launch_dependents();  // the loads are in: the next kernel may start taking SMs as these blocks retire
     warp_layernorm<NV>(v, g, b, lane, eps);
     store_row<NV, OUT_F32>(v, out, r, lane);
 }
@@ -85,6 +87,7 @@ vit_assemble_kernel(const float* __restrict__ emb, const float* __restrict__ cls
                     int L, const float* __restrict__ g, const float* __restrict__ b, float eps, float* __restrict__ x) {
     const int lane = threadIdx.x & 31;
     const int64_t r = int64_t(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+    pdl_wait();
     if (r >= rows) return;
     const int64_t bi = r / L;
     const int l = int(r % L);
@@ -108,6 +111,7 @@ text_embed_kernel(const int64_t* __restrict__ text, const float* __restrict__ to
                   int L, int vocab, float* __restrict__ x) {
     const int lane = threadIdx.x & 31;
     const int64_t r = int64_t(blockIdx.x) * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+    pdl_wait();
     if (r >= rows) return;
     int64_t id = text[r];
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);  // ids are validated on the host side of the ABI; never read outside the table
@@ -126,6 +130,7 @@ text_embed_kernel(const int64_t* __restrict__ text, const float* __restrict__ to
 __global__ void text_eos_kernel(const int64_t* __restrict__ text, const uint8_t* __restrict__ pad, int64_t B, int L,
                                 int64_t eot_id, int32_t* __restrict__ eos, uint8_t* __restrict__ new_mask) {
     const int64_t b = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    pdl_wait();
     if (b >= B) return;
     const int64_t* t = text + b * L;
     int best = 0;
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, int64_t B, int C, int R, int P, __nv_bfloat16* __restrict__ out) {
     const int g = R / P, xv = R / 8;
     const int64_t total = B * C * R * xv;
+    pdl_wait();
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
         const int x8 = int(i % xv);
         const int y = int((i / xv) % R);
@@ -162,9 +168,8 @@ patchify_kernel(const float* __restrict__ img, int64_t B, int C, int R, int P, _
 template <int NV, bool OUT_F32>
 int launch_ln(const float* x, int64_t rows, int64_t row_mul, const int32_t* row_idx, const float* g, const float* b, float eps,
               void* out, cudaStream_t st) {
-    layernorm_kernel<NV, OUT_F32><<<unsigned(ceil_div(rows, ROWS_PER_BLOCK)), ROWS_PER_BLOCK * 32, 0, st>>>(
-        x, rows, row_mul, row_idx, g, b, eps, out);
-    CMH_LAUNCH_CHECK("layernorm_kernel");
+    CMH_CUDA_TRY(launch_kernel(layernorm_kernel<NV, OUT_F32>, dim3(unsigned(ceil_div(rows, ROWS_PER_BLOCK))),
+                               dim3(ROWS_PER_BLOCK * 32), 0, st, 1, x, rows, row_mul, row_idx, g, b, eps, out));
     return CMH_OK;
 }
 
@@ -197,8 +202,8 @@ int vit_assemble(const float* emb, const float* cls, const float* pos, int64_t B
                  float eps, float* x, cudaStream_t st) {
     const int64_t rows = B * L;
     const unsigned grid = unsigned(ceil_div(rows, ROWS_PER_BLOCK));
-    CMH_DISPATCH_NV(D, (vit_assemble_kernel<NV><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(emb, cls, pos, rows, L, g, b, eps, x)));
-    CMH_LAUNCH_CHECK("vit_assemble_kernel");
+    CMH_DISPATCH_NV(D, CMH_CUDA_TRY(launch_kernel(vit_assemble_kernel<NV>, dim3(grid), dim3(ROWS_PER_BLOCK * 32), 0, st, 1, emb, cls,
+                                                  pos, rows, L, g, b, eps, x)));
     return CMH_OK;
 }
 
@@ -206,15 +211,15 @@ int text_embed(const int64_t* text, const float* tok, const float* pos, int64_t 
                cudaStream_t st) {
     const int64_t rows = B * L;
     const unsigned grid = unsigned(ceil_div(rows, ROWS_PER_BLOCK));
-    CMH_DISPATCH_NV(D, (text_embed_kernel<NV><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(text, tok, pos, rows, L, vocab, x)));
-    CMH_LAUNCH_CHECK("text_embed_kernel");
+    CMH_DISPATCH_NV(D, CMH_CUDA_TRY(launch_kernel(text_embed_kernel<NV>, dim3(grid), dim3(ROWS_PER_BLOCK * 32), 0, st, 1, text, tok,
+                                                  pos, rows, L, vocab, x)));
     return CMH_OK;
 }
 
 int text_eos(const int64_t* text, const uint8_t* pad, int64_t B, int L, int64_t eot_id, int32_t* eos, uint8_t* new_mask,
              cudaStream_t st) {
-    text_eos_kernel<<<unsigned(ceil_div(B, 128)), 128, 0, st>>>(text, pad, B, L, eot_id, eos, new_mask);
-    CMH_LAUNCH_CHECK("text_eos_kernel");
+    CMH_CUDA_TRY(launch_kernel(text_eos_kernel, dim3(unsigned(ceil_div(B, 128))), dim3(128), 0, st, 1, text, pad, B, L, eot_id, eos,
+                               new_mask));
     return CMH_OK;
 }
 
@@ -224,8 +229,8 @@ int patchify(const float* img, int64_t B, int C, int R, int P, void* out, cudaSt
     const int64_t total = B * C * R * (R / 8);
     const int64_t blocks = ceil_div(total, 256);
     const int64_t cap = int64_t(sm_count_cached()) * 32;
-    patchify_kernel<<<unsigned(blocks < cap ? blocks : cap), 256, 0, st>>>(img, B, C, R, P, static_cast<__nv_bfloat16*>(out));
-    CMH_LAUNCH_CHECK("patchify_kernel");
+    CMH_CUDA_TRY(launch_kernel(patchify_kernel, dim3(unsigned(blocks < cap ? blocks : cap)), dim3(256), 0, st, 1, img, B, C, R, P,
+                               static_cast<__nv_bfloat16*>(out)));
     return CMH_OK;
 }
 

@@ -187,6 +187,11 @@ int cmh_gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* 
 /* Test / tuning hook: pin the tile width (128, 192, 256; 0 = automatic) and the CTA group (1 = one SM per tile,
  * 2 = tcgen05 cta_group::2 pairs on 256-row tiles; 0 = automatic) of every following cmh_gemm_bf16 call. */
 int cmh_gemm_force_tile(int bn, int cta_group);
+/* Debug timeline: when non-NULL, every following GEMM writes SM clock stamps into device_buffer[cta][64]
+ * (0 entry, 1 set-up done, 2+4i.. per tile: accumulator wait / free / first operands landed / all MMAs issued,
+ * 34+2i.. epilogue start / end of tile i, 63 exit). */
+int cmh_gemm_set_trace(long long* device_buffer);
+int cmh_gemm_force_units(int units); /* debug: cap the persistent grid at `units` CTAs (pairs for cta_group 2); 0 = all SMs */
 
 
 /* ---- E: CLIP encoders (models/CLIP/model.py) ---------------------------------------------------------------------

@@ -28,6 +28,13 @@ def run_gemm(a, w, bias, epi, resid=None):
     return out
 
 
+def gelu_slack(a, w, bias):
+    """QuickGELU is evaluated as 0.5x + 0.5x*tanh(0.851x) with MUFU tanh.approx (relative error 2^-11 on the tanh):
+    absolute error <= 2.5e-4 |x| on the pre-activation x, before the bf16 rounding of the result."""
+    x = a.float() @ w.float().t() + (0 if bias is None else bias)
+    return 3e-4 * x.abs() + 1e-6
+
+
 def reference(a, w, bias, epi, resid=None):
     acc = a.float() @ w.float().t()
     if bias is not None:
@@ -62,6 +69,8 @@ def test_gemm_matches_fp32_reference(M, N, K, epi):
     mass = a.float().abs() @ w.float().abs().t() + 1.0
     err = (got - want).abs()
     tol = 2e-5 * mass + (2.0 ** -8) * want.abs() * (1 if epi in (EPI_BF16, EPI_GELU_BF16) else 0) + 1e-6
+    if epi == EPI_GELU_BF16:
+        tol = tol + gelu_slack(a, w, bias)
     assert bool((err <= tol).all()), (float(err.max()), float((err / tol).max()))
     # no bias / in-place residual variants
     if epi == EPI_F32:
@@ -87,7 +96,7 @@ def test_gemm_every_tile_configuration(bn, cg, M, N, K, epi):
     mass = a.float().abs() @ w.float().abs().t() + 1.0
     tol = 2e-5 * mass + (2.0 ** -8) * want.abs() * (1 if epi in (EPI_BF16, EPI_GELU_BF16) else 0) + 1e-6
     if epi == EPI_GELU_BF16:
-        tol = tol + 2e-6 * want.abs() + 1e-6   # MUFU.EX2/RCP sigmoid: 2 ulp before the bf16 rounding
+        tol = tol + gelu_slack(a, w, bias)
     assert bool(((got - want).abs() <= tol).all()), float(((got - want).abs() / tol).max())
 
 
