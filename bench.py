@@ -145,7 +145,102 @@ def run_reference(args, cfg, name):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_encode:
+        iv, idt = cpu_encode_images_per_sec(8)
+        line["encode"] = {"metric": "clip_encode_images_per_sec", "value": iv, "unit": "img/s", "impl": "reference",
+                          "cpu_baseline": {"value": iv, "unit": "img/s", "cores": cores, "kind": "port",
+                                           "sample": "8 images through the fp32 CPU restatement of encode_image, %.1f s" % idt}}
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CLIP ViT-B/32 encode (second half of BASELINE.json's metric: imgs/sec), batch 256 per GPU
+# ---------------------------------------------------------------------------------------------------------
+ENCODE_BATCH = 256
+
+
+def tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops_sustained"]), float(d["bf16_tflops"]), "measured"
+    except Exception:
+        return 1400.0, 1590.0, "fallback"
+
+
+def cpu_encode_images_per_sec(n_images=8):
+    """The reference's fp32 CPU path (oracle/clip_port.py restates models/CLIP/model.py:232-268) on a few images."""
+    from oracle import clip_port as port
+
+    sd = synth.clip_state_dict(synth.VIT_B32, seed=0)
+    image = synth.random_images(n_images, seed=1)
+    with torch.no_grad():
+        port.encode_image(sd, image[:2])
+        t0 = time.perf_counter()
+        port.encode_image(sd, image)
+        dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def bench_encode(args, dev, world, rank, barrier, all_max):
+    """DSPH-style get_code step on random-init ViT-B/32: images -> CLIP tower -> hash head -> packed 64-bit codes."""
+    from clip_based_cross_modal_hash_b200 import models
+    from oracle import clip_port as port
+
+    B = ENCODE_BATCH
+    sd = synth.clip_state_dict(synth.VIT_B32, seed=0)
+    model = models.DSPH(sd, synth.dsph_head_state_dict(512, 64, seed=1), device=dev)
+    nbuf = 3  # 3 x 154 MB of images > 126 MB L2: every step reads its batch from HBM
+    host_img = [synth.random_images(B, seed=10 + i + 100 * rank).pin_memory() for i in range(nbuf)]
+    text, _ = synth.random_captions(B, seed=20 + rank)
+    host_txt = text.pin_memory()
+    d_img = [t.to(dev) for t in host_img]
+    d_txt = host_txt.to(dev)
+    steps, warm = args.steps, max(args.warmup, 3)
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for i in range(warm):
+        model.encode_image_packed(d_img[i % nbuf])
+        model.encode_text_packed(d_txt)
+    img_ms = all_max(timed(lambda i: model.encode_image_packed(d_img[i % nbuf]), steps)) / steps
+    txt_ms = all_max(timed(lambda i: model.encode_text_packed(d_txt), steps)) / steps
+    # the image tower alone (without head/pack) for the tensor-pipe roofline
+    tower_ms = all_max(timed(lambda i: model.backbone.encode_image(d_img[i % nbuf]), steps)) / steps
+    # end to end: models.get_code over host (pinned) batches, H2D inside the timed region, packed codes read back
+    loader = [(host_img[i % nbuf], host_txt, None, None, torch.arange(B) + B * i) for i in range(steps)]
+    models.get_code(model, loader[:2], 2 * B, dev)
+    barrier()
+    t0 = time.perf_counter()
+    ci, ct = models.get_code(model, loader, steps * B, dev)
+    codes_host = ci.cpu()
+    e2e_ms = all_max((time.perf_counter() - t0) * 1e3) / steps
+    sustained, burst, kind = tensor_peak()
+    fl = port.flops_image()
+    ach = fl * B / (tower_ms * 1e-3) / 1e12
+    out = {
+        "metric": "clip_encode_images_per_sec", "value": B * world / (img_ms * 1e-3), "unit": "img/s", "batch_per_gpu": B,
+        "ms_per_batch": img_ms, "what": "DSPH get_code step: fp32 NCHW images (resident in HBM) -> ViT-B/32 tower (bf16 tcgen05 GEMMs, "
+        "fp32 residual stream) -> tanh head -> 64-bit packed codes; random-init weights, synthetic images",
+        "text": {"value": B * world / (txt_ms * 1e-3), "unit": "captions/s", "ms_per_batch": txt_ms, "tokens": 32},
+        "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "image+caption pairs/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 32 * 8 + B * 8, "d2h_bytes_per_step": int(codes_host.numel() * 4 // steps),
+                "what": "models.get_code over pinned host batches (image + caption), copies overlapped on a side stream"},
+        "roofline": {"bound": "tensor", "kernel": "image tower (12 blocks, 50 tokens)", "achieved": ach, "peak": sustained,
+                     "unit": "TFLOP/s", "frac": ach / sustained, "frac_of_burst_peak": ach / burst, "peak_kind": kind + " cuBLAS bf16, sustained",
+                     "traffic": None, "algorithmic_flops_per_image": fl, "tower_ms": tower_ms},
+        "gpu_launches_per_step": 12 * 7 + 7,
+    }
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -285,6 +380,20 @@ def run_ours(args, cfg, name):
     value = pairs_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = pairs_per_step * len(e2e_ms) / (e2e_total_ms * 1e-3)
 
+    def all_max(v):
+        tt = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    encode = None
+    if not args.no_encode:
+        del d_qB, d_rB, d_qL, d_rL, flush
+        torch.cuda.empty_cache()
+        with ClockSampler(local_rank) as enc_clocks:
+            encode = bench_encode(args, dev, world, rank, barrier, all_max)
+        encode["clocks"] = enc_clocks.summary()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -303,6 +412,8 @@ def run_ours(args, cfg, name):
         "gpu_launches": args.steps * 10,
         "clocks": clocks.summary(),
     }
+    if encode is not None:
+        line["encode"] = encode
     if world == 1:
         names = (["pack", "hist_kernel", "scan", "rank_map_kernel", "map_finish"] if args.op == "map"
                  else ["pack", "hist_kernel", "scan", "rank_topk_kernel", "none"])
@@ -331,6 +442,10 @@ def run_ours(args, cfg, name):
         v, per = cpu_reference_pairs_per_sec(cfg, sample_q, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "%d of %d queries x %d gallery items, %.1f s" % (sample_q, Q, N, per)}
+        if encode is not None:
+            iv, idt = cpu_encode_images_per_sec(8)
+            encode["cpu_baseline"] = {"value": iv, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+                                      "sample": "8 images through the fp32 CPU restatement of encode_image, %.1f s" % idt}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -343,6 +458,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--no-encode", action="store_true", help="skip the CLIP encode section of the line")
     ap.add_argument("--op", default=None, choices=["map", "topk"],
                     help="map = calc_map_k (default for C1-C3); topk = Hamming + per-query top-k (default for C4-*)")
     args = ap.parse_args()

@@ -181,3 +181,47 @@ class DCMHT(_Model):
     def make_hash_code(code):               # runners/DCMHT/runner.py:83-95
         pairs = code.reshape(code.shape[0], -1, 2)   # argmax over (2j, 2j+1); a tie picks index 0 -> -1
         return torch.where(pairs[..., 1] > pairs[..., 0], 1.0, -1.0)
+
+
+def get_code(model, data_loader, length: int, device=None):
+    """Drop-in for ``BaseTrainer.get_code`` (runners/base.py:242-266) that stays bit-packed.
+
+    ``data_loader`` yields the reference's batches ``(image, text, key_padding_mask, label, index)`` (host tensors,
+    ideally pinned).  Returns ``(img_codes, txt_codes)``: int32 ``[length, W]`` device tensors in the evaluator's packed
+    layout, row ``index[i]`` of each buffer holding sample i's code — what ``calc_utils.calc_map_k`` consumes directly
+    (no +-1 fp32 ``[length, K]`` buffers, no device->host hop).  The host->device copy of batch i+1
+    runs on a side stream while batch i is encoded.
+    """
+    dev = torch.device(device) if device is not None else model.backbone.device_
+    W = _words(model.output_dim)
+    img_buf = torch.zeros((length, W), dtype=torch.int32, device=dev)
+    txt_buf = torch.zeros((length, W), dtype=torch.int32, device=dev)
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)
+
+    def stage(batch):
+        image, text, _mask, _label, index = batch
+        with torch.cuda.stream(side):
+            item = (image.to(dev, non_blocking=True), text.to(dev, non_blocking=True),
+                    torch.as_tensor(index).to(dev, non_blocking=True).long())
+            done = torch.cuda.Event()
+            done.record(side)
+        return item, done
+
+    def encode(staged):
+        (image, text, index), done = staged
+        main.wait_event(done)
+        for t in (image, text, index):
+            t.record_stream(main)
+        img_buf[index] = model.encode_image_packed(image)
+        txt_buf[index] = model.encode_text_packed(text)
+
+    pending = None
+    for batch in data_loader:
+        nxt = stage(batch)
+        if pending is not None:
+            encode(pending)
+        pending = nxt
+    if pending is not None:
+        encode(pending)
+    return img_buf, txt_buf

@@ -201,6 +201,23 @@ def test_model_codes_agree_with_oracle(method):
             assert np.array_equal(bits.astype(np.float32) * 2 - 1, code.numpy())
 
 
+def test_get_code_matches_batchwise_encoding():
+    """models.get_code (pipelined H2D, scatter by dataset index) == per-batch packed encoding, rows placed by `index`."""
+    nbits, B, nb = 32, 5, 3
+    sd = synth.clip_state_dict(synth.TINY, seed=8)
+    model = models.DSPH(sd, synth.dsph_head_state_dict(synth.TINY["embed_dim"], nbits, seed=9))
+    perm = torch.randperm(B * nb, generator=torch.Generator().manual_seed(0))
+    loader = []
+    for i in range(nb):
+        text, pad = synth.random_captions(B, seed=40 + i, vocab=synth.TINY["vocab_size"])
+        loader.append((synth.random_images(B, seed=30 + i).pin_memory(), text.pin_memory(), pad, None, perm[i * B:(i + 1) * B]))
+    img_codes, txt_codes = models.get_code(model, loader, B * nb)
+    assert img_codes.shape == (B * nb, 1) and img_codes.dtype == torch.int32
+    for image, text, _, _, index in loader:
+        assert torch.equal(img_codes[index.cuda()], model.encode_image_packed(image))
+        assert torch.equal(txt_codes[index.cuda()], model.encode_text_packed(text))
+
+
 def test_encoder_rejects_bad_arguments():
     sd = synth.clip_state_dict(synth.TINY, seed=1)
     bb = encoder.ClipBackbone(sd)
