@@ -29,13 +29,17 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;              // two per TMEM lane quarter: they hide each other's TMEM / TMA-store latency
+constexpr int MMA_LOOKAHEAD = 2;  // k-blocks (of 4 MMAs) in flight in the tensor pipe
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1, TMEM_WARP = EPI_WARPS + 2;
 // The latency-critical single-thread roles get the HIGHEST warp ids: the SM's warp arbiter prefers higher ids, and with
 // the epilogue warps above them the MMA issue loop lost ~20 % once an epilogue ran concurrently (profiles/README.md).
 constexpr int GEMM_THREADS = (EPI_WARPS + 3) * 32;
 constexpr int STG_CHUNK_BYTES = 4096;     // one epilogue chunk: 32 rows x 128 B (64 bf16 or 32 fp32 columns), SWIZZLE_128B
-constexpr int STG_WARP_BYTES = 2 * STG_CHUNK_BYTES;  // double buffered per warp
-constexpr int SMEM_BUDGET = 227 * 1024 - EPI_WARPS * STG_WARP_BYTES - EPI_WARPS * 256 * 4 - 1024 - 256;  // operand ring
+// One staging buffer per warp.  The epilogue leaves through ordinary coalesced 16-byte stores / vector reductions, not TMA:
+// a TMA store queues behind the operand loads in the SM's TMA unit, and with a deep operand ring its shared-memory read
+// took ~2000 clk, which made the epilogue 3x slower than the main loop (profiles/README.md).
+constexpr int STG_WARP_BYTES = STG_CHUNK_BYTES;
+constexpr int SMEM_BUDGET = 227 * 1024 - EPI_WARPS * STG_WARP_BYTES - 1024 - 256;  // operand ring
 
 template <int BN, int CG>
 struct GemmCfg {
@@ -45,7 +49,7 @@ struct GemmCfg {
     static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES < 8 ? SMEM_BUDGET / STAGE_BYTES : 8;
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int SMEM_BYTES = RING_BYTES + EPI_WARPS * STG_WARP_BYTES + EPI_WARPS * 256 * 4 /*bias*/ + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = RING_BYTES + EPI_WARPS * STG_WARP_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -57,6 +61,9 @@ struct GemmParams {
     int64_t ldr;
     int epi;
     int tiles_m, tiles_n;
+    // work items: [0, tail_start) are full (CG*128) x BN tiles; the tiles of the last, partial wave are cut into
+    // 2^tail_shift column slices each (one item per slice) so that the wave ends after a slice, not after a tile
+    int tail_start, tail_shift, num_items;
     long long* trace;  // debug timeline (cmh_gemm_set_trace): [cta][64] SM clock stamps, or null
 };
 
@@ -136,6 +143,20 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void stg128(void* gptr, uint4 v) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// x[0..3] += v : one 16-byte fp32 vector reduction at L2 (the residual stream add of model.py:195-196)
+__device__ __forceinline__ void red_add_f32x4(void* gptr, uint4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                 "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -232,6 +253,13 @@ __device__ __forceinline__ float quick_gelu(float x) {
     const float h = 0.5f * x;
     return fmaf(h, t, h);
 }
+template <int N>
+__device__ __forceinline__ float pick_bias(const float (&b)[N], int i) {  // register array, runtime index
+    float v = b[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) v = i == k ? b[k] : v;
+    return v;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -240,13 +268,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
     using C = GemmCfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stg_all = smem + C::RING_BYTES;                                           // EPI_WARPS x 8 KB, 1024-aligned
-    float* bias_all = reinterpret_cast<float*>(stg_all + EPI_WARPS * STG_WARP_BYTES);  // EPI_WARPS x 256 floats
-    uint64_t* full = reinterpret_cast<uint64_t*>(bias_all + EPI_WARPS * 256);
+    uint8_t* stg_all = smem + C::RING_BYTES;  // EPI_WARPS x 4 KB, 1024-aligned
+    uint64_t* full = reinterpret_cast<uint64_t*>(stg_all + EPI_WARPS * STG_WARP_BYTES);
     uint64_t* empty = full + C::STAGES;
     uint64_t* tfull = empty + C::STAGES;
     uint64_t* tempty = tfull + 2;
@@ -257,13 +284,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == MMA_WARP * 32) CMH_TRACE(0);
     const int unit = CG == 1 ? int(blockIdx.x) : int(blockIdx.x >> 1);
     const int units = CG == 1 ? int(gridDim.x) : int(gridDim.x >> 1);
-    const int num_tiles = p.tiles_m * p.tiles_n;  // tiles of (CG*128) x BN
+    const int num_items = p.num_items;
     const int kblocks = int((p.K + BK - 1) / BK);
+    // item -> (row block, first column, width)
+    auto decode = [&](int j, int& m_idx, int& n_first, int& width) {
+        int tile = j, sub = 0;
+        width = BN;
+        if (j >= p.tail_start) {
+            const int r = j - p.tail_start;
+            tile = p.tail_start + (r >> p.tail_shift);
+            sub = r & ((1 << p.tail_shift) - 1);
+            width = BN >> p.tail_shift;
+        }
+        m_idx = tile % p.tiles_m;
+        n_first = (tile / p.tiles_m) * BN + sub * width;
+    };
 
     if (warp == PRODUCER_WARP && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
-        prefetch_tmap(&tmO);
+        prefetch_tmap(&tmB2);
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full[s], 1);   // the leader's arrive.expect_tx; bytes come from both CTAs' TMA loads
             mbar_init(&empty[s], 1);  // tcgen05.commit (multicast to both CTAs when CG = 2)
@@ -287,21 +327,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == PRODUCER_WARP) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = unit; t < num_tiles; t += units) {
-            const int m0 = (t % p.tiles_m) * (BM * CG) + int(rank) * BM;
-            const int n0 = (t / p.tiles_m) * BN + int(rank) * (BN / CG);
+        for (int t = unit; t < num_items; t += units) {
+            int m_idx, n_first, width;
+            decode(t, m_idx, n_first, width);
+            const int m0 = m_idx * (BM * CG) + int(rank) * BM;
+            const int n0 = n_first + int(rank) * (width / CG);
+            const CUtensorMap* mapB = width == BN ? &tmB : &tmB2;  // box = width/CG rows of W
+            const uint32_t stage_tx = uint32_t(C::A_BYTES + (width / CG) * BK * 2);
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1u);
                 if (elect_one()) {
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     if (CG == 1) {
-                        mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                        mbar_arrive_expect_tx(&full[stage], stage_tx);
                         tma_load_2d(sa, &tmA, kb * BK, m0, &full[stage]);
-                        tma_load_2d(sa + C::A_BYTES, &tmB, kb * BK, n0, &full[stage]);
+                        tma_load_2d(sa + C::A_BYTES, mapB, kb * BK, n0, &full[stage]);
                     } else {
-                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * stage_tx);
                         tma_load_2d_pair(sa, &tmA, kb * BK, m0, &full[stage]);
-                        tma_load_2d_pair(sa + C::A_BYTES, &tmB, kb * BK, n0, &full[stage]);
+                        tma_load_2d_pair(sa + C::A_BYTES, mapB, kb * BK, n0, &full[stage]);
                     }
                 }
                 __syncwarp();
@@ -310,11 +354,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == MMA_WARP) {
         if (rank == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int t = unit; t < num_tiles; t += units, ++it) {
+            int it = 0, issued = 0;
+            for (int t = unit; t < num_items; t += units, ++it) {
+                const uint32_t idesc = make_idesc_bf16(BM * CG, t >= p.tail_start ? (BN >> p.tail_shift) : BN);
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 if (lane == 0) CMH_TRACE(2 + it * 4);
@@ -322,7 +366,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 if (lane == 0) CMH_TRACE(3 + it * 4);
                 const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = 0; kb < kblocks; ++kb, ++issued) {
+                    // Keep at most MMA_LOOKAHEAD k-blocks queued in the tensor pipe.  tcgen05.ld of the epilogue warps is
+                    // served in order behind the queued MMAs: with the whole 6-stage ring issued ahead, every TMEM load
+                    // waited ~3000 clk and the epilogue fell behind the main loop (profiles/README.md).
+                    if (issued >= MMA_LOOKAHEAD) {
+                        const int g = issued - MMA_LOOKAHEAD;
+                        mbar_wait(&empty[g % C::STAGES], uint32_t(g / C::STAGES) & 1u);
+                    }
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     if (kb == 0 && lane == 0) CMH_TRACE(4 + it * 4);
@@ -352,62 +403,60 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int e = warp, q = warp & 3, half = e >> 2;
         const bool out_bf16 = p.epi == CMH_EPI_BF16 || p.epi == CMH_EPI_GELU_BF16;
         const int cw = out_bf16 ? 64 : 32;  // columns per chunk
-        const uint32_t stg = smem_u32(stg_all + e * STG_WARP_BYTES);
-        const uint32_t bias_s = smem_u32(bias_all + e * 256);
+        const uint32_t buf = smem_u32(stg_all + e * STG_WARP_BYTES);
+        const uint32_t rowp = buf + lane * 128;
+        const int sw = lane & 7;  // 16-byte chunk index ^= row & 7: conflict-free row writes and row reads
+        const int esz = out_bf16 ? 2 : 4;
         int it = 0;
-        uint32_t chunk_no = 0;
-        for (int t = unit; t < num_tiles; t += units, ++it) {
+        for (int t = unit; t < num_items; t += units, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            const int m0 = (t % p.tiles_m) * (BM * CG) + int(rank) * BM, n0 = (t / p.tiles_m) * BN;
-            for (int j = lane; j < BN; j += 32) sts32f(bias_s + j * 4, (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f);
-            __syncwarp();
+            int m_idx, n0, width;
+            decode(t, m_idx, n0, width);
+            const int m0 = m_idx * (BM * CG) + int(rank) * BM;
+            // Bias of this warp's 32-column groups, one column per lane, fetched BEFORE the accumulator is ready: while the
+            // operand ring is in flight a global load from this SM queues behind ~190 KB of TMA traffic (~3000 clk), and
+            // loading the bias inside the chunk loop made the epilogue 4x slower than the main loop (profiles/README.md).
+            constexpr int NB = 2 * ((BN + 127) / 128);  // 32-column groups one warp can own (alternate 128-byte chunks)
+            float breg[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int gcol = n0 + (out_bf16 ? (half + 2 * (i >> 1)) * 64 + (i & 1) * 32 : (half + 2 * i) * 32) + lane;
+                breg[i] = (p.bias && gcol < p.N) ? __ldg(p.bias + gcol) : 0.f;
+            }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             if (e == 0 && lane == 0) CMH_TRACE(34 + it * 2);
+            int grp = 0;  // index of the current 32-column group in breg
 #pragma unroll 1
-            for (int c0 = half * cw; c0 < BN; c0 += 2 * cw) {
+            for (int c0 = half * cw; c0 < width; c0 += 2 * cw) {
                 if (n0 + c0 >= p.N) break;  // remaining chunks lie outside the matrix (uniform)
-                const uint32_t buf = stg + (chunk_no & 1u) * STG_CHUNK_BYTES;
-                ++chunk_no;
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + c0);
-                const uint32_t rowp = buf + lane * 128;
-                const int sw = lane & 7;  // SWIZZLE_128B: 16-byte chunk index ^= row & 7
                 uint32_t r[32];
                 tmem_ld32(taddr, r);
-                if (lane == 0) bulk_wait_read<1>();  // the store that last used this buffer has finished reading it
-                __syncwarp();
                 if (out_bf16) {
+                    uint32_t pk[32];
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         if (hh == 1) tmem_ld32(taddr + 32, r);
                         float v[32];
+                        const float bl = pick_bias<NB>(breg, grp++);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b = lds128f(bias_s + (c0 + hh * 32 + j) * 4);
-                            v[j] = __uint_as_float(r[j]) + b.x, v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
-                            v[j + 2] = __uint_as_float(r[j + 2]) + b.z, v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
                         if (p.epi == CMH_EPI_GELU_BF16) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
                         }
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            uint4 o;
-                            o.x = pack_bf16(v[8 * c], v[8 * c + 1]), o.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
-                            o.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]), o.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
-                            sts128(rowp + (((hh * 4 + c) ^ sw) << 4), o.x, o.y, o.z, o.w);
-                        }
+                        for (int j = 0; j < 16; ++j) pk[hh * 16 + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
                     }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) sts128(rowp + ((c ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 } else {
                     float v[32];
+                    const float bl = pick_bias<NB>(breg, grp++);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = lds128f(bias_s + (c0 + j) * 4);
-                        v[j] = __uint_as_float(r[j]) + b.x, v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
-                        v[j + 2] = __uint_as_float(r[j + 2]) + b.z, v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
-                    }
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
                     if (p.epi == CMH_EPI_TANH_F32) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
@@ -417,13 +466,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         sts128(rowp + ((c ^ sw) << 4), __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
                                __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
                 }
-                fence_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    if (p.epi == CMH_EPI_RESID_F32) tma_reduce_add_2d(&tmO, n0 + c0, m0 + q * 32, buf);
-                    else tma_store_2d(&tmO, n0 + c0, m0 + q * 32, buf);
-                    bulk_commit();
+                // staging -> global: 8 lanes cover one 128-byte row, a warp instruction writes 4 full rows
+                {
+                    const int c16 = lane & 7;
+                    const int col = n0 + c0 + c16 * (16 / esz);
+                    const bool col_ok = col < p.N;  // N is a multiple of the 16-byte vector (checked on the host)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + (lane >> 3);
+                        const int64_t grow = int64_t(m0) + q * 32 + row;
+                        const uint4 v = lds128(buf + row * 128 + ((c16 ^ (row & 7)) << 4));
+                        if (col_ok && grow < p.M) {
+                            uint8_t* dst = static_cast<uint8_t*>(p.out) + (grow * p.ldo + col) * esz;
+                            if (p.epi == CMH_EPI_RESID_F32) red_add_f32x4(dst, v);
+                            else stg128(dst, v);
+                        }
+                    }
                 }
+                __syncwarp();  // the buffer is free again
             }
             tc_fence_before();
             __syncwarp();
@@ -433,7 +494,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (e == 0) CMH_TRACE(35 + it * 2);
             }
         }
-        if (lane == 0) bulk_wait_read<0>();
     }
     tc_fence_before();
     __syncwarp();
@@ -446,7 +506,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 long long* g_trace = nullptr;
-int g_force_bn = 0, g_force_cg = 0, g_force_units = 0;  // test/bench hook (cmh_gemm_force_tile): 0 = automatic
+int g_force_bn = 0, g_force_cg = 0, g_force_units = 0;
+bool g_tail_slicing = true;  // test/bench hook (cmh_gemm_force_tile): 0 = automatic
 
 // ---- host side ----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -498,7 +559,7 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
 }
 
 template <int BN, int CG>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, GemmParams p, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& ta, const void* W, int64_t ldw, const CUtensorMap& to, GemmParams p, cudaStream_t st) {
     using C = GemmCfg<BN, CG>;
     static bool configured = false;
     if (!configured) {
@@ -510,8 +571,26 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     const int tiles = p.tiles_m * p.tiles_n;
     int units = sm_count_cached() / CG;
     if (g_force_units > 0 && g_force_units < units) units = g_force_units;
-    CMH_CUDA_TRY(launch_kernel(gemm_bf16_kernel<BN, CG>, dim3(unsigned((tiles < units ? tiles : units) * CG)), dim3(GEMM_THREADS),
-                               C::SMEM_BYTES, st, CG, ta, tb, to, p));
+    // Tail slicing: the R tiles of the last partial wave become R * 2^shift column slices on as many units.  A slice is
+    // at least one epilogue chunk wide (64 bf16 / 32 fp32 columns) and the slices must fit one wave.
+    const bool out_bf16 = p.epi == CMH_EPI_BF16 || p.epi == CMH_EPI_GELU_BF16;
+    const int rem = tiles % units;
+    int shift = 0;
+    if (g_tail_slicing && tiles > units && rem > 0) {
+        const int min_w = out_bf16 ? 64 : 32;
+        while ((BN >> (shift + 1)) >= min_w && (BN >> (shift + 1)) % min_w == 0 && (BN >> (shift + 1)) % (16 * CG) == 0 &&
+               (rem << (shift + 1)) <= units)
+            ++shift;
+    }
+    p.tail_shift = shift;
+    p.tail_start = shift ? tiles - rem : tiles;
+    p.num_items = p.tail_start + ((tiles - p.tail_start) << shift);
+    CUtensorMap tb, tb2;
+    if (int rc = make_tmap(&tb, W, p.N, p.K, ldw, BN / CG)) return rc;
+    if (int rc = make_tmap(&tb2, W, p.N, p.K, ldw, (BN >> shift) / CG)) return rc;
+    const int grid_units = p.num_items < units ? p.num_items : units;
+    CMH_CUDA_TRY(launch_kernel(gemm_bf16_kernel<BN, CG>, dim3(unsigned(grid_units * CG)), dim3(GEMM_THREADS), C::SMEM_BYTES, st, CG,
+                               ta, tb, tb2, to, p));
     return CMH_OK;
 }
 
@@ -540,6 +619,8 @@ int gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, i
     CMH_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "gemm: leading dimensions must be multiples of 8 elements");
     CMH_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemm: operands must be 16-byte aligned");
     CMH_REQUIRE(epi >= CMH_EPI_BF16 && epi <= CMH_EPI_TANH_F32, "gemm: unknown epilogue %d", epi);
+    CMH_REQUIRE(N % ((epi == CMH_EPI_BF16 || epi == CMH_EPI_GELU_BF16) ? 8 : 4) == 0,
+                "gemm: N = %lld must be a multiple of the 16-byte output vector", (long long)N);
     CMH_REQUIRE(epi != CMH_EPI_RESID_F32 || resid, "gemm: residual epilogue needs resid");
     const bool out_bf16 = epi == CMH_EPI_BF16 || epi == CMH_EPI_GELU_BF16;
     CMH_REQUIRE(ldo % (out_bf16 ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: output must be 16-byte aligned per row");
@@ -549,24 +630,23 @@ int gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, i
     pick_tile(M, N, &bn, &cg);
     if (g_force_bn > 0) bn = g_force_bn;
     if (g_force_cg > 0) cg = g_force_cg;
-    CUtensorMap ta, tb, to;
+    CUtensorMap ta, to;
     if (int rc = make_tmap(&ta, A, M, K, lda, BM)) return rc;
-    if (int rc = make_tmap(&tb, W, N, K, ldw, bn / cg)) return rc;
     if (int rc = make_out_tmap(&to, out, M, N, ldo, out_bf16)) return rc;
     GemmParams p{};
     p.M = M, p.N = N, p.K = K, p.bias = bias, p.out = out, p.ldo = ldo, p.resid = resid, p.ldr = ldr, p.epi = epi;
     p.trace = g_trace;
     if (cg == 2) {
         switch (bn) {
-            case 256: return launch_gemm<256, 2>(ta, tb, to, p, st);
-            case 192: return launch_gemm<192, 2>(ta, tb, to, p, st);
-            default: return launch_gemm<128, 2>(ta, tb, to, p, st);
+            case 256: return launch_gemm<256, 2>(ta, W, ldw, to, p, st);
+            case 192: return launch_gemm<192, 2>(ta, W, ldw, to, p, st);
+            default: return launch_gemm<128, 2>(ta, W, ldw, to, p, st);
         }
     }
     switch (bn) {
-        case 256: return launch_gemm<256, 1>(ta, tb, to, p, st);
-        case 192: return launch_gemm<192, 1>(ta, tb, to, p, st);
-        default: return launch_gemm<128, 1>(ta, tb, to, p, st);
+        case 256: return launch_gemm<256, 1>(ta, W, ldw, to, p, st);
+        case 192: return launch_gemm<192, 1>(ta, W, ldw, to, p, st);
+        default: return launch_gemm<128, 1>(ta, W, ldw, to, p, st);
     }
 }
 
@@ -581,6 +661,11 @@ extern "C" int cmh_gemm_force_tile(int bn, int cta_group) {
     if (!(bn == 0 || bn == 128 || bn == 192 || bn == 256) || cta_group < 0 || cta_group > 2)
         return cmh::fail(CMH_ERR_INVALID, "gemm_force_tile: bn in {0,128,192,256}, cta_group in {0,1,2}");
     cmh::g_force_bn = bn, cmh::g_force_cg = cta_group;
+    return CMH_OK;
+}
+
+extern "C" int cmh_gemm_tail_slicing(int on) {  // debug: 0 = every tile of the last wave stays whole
+    cmh::g_tail_slicing = on != 0;
     return CMH_OK;
 }
 
