@@ -24,7 +24,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
     const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
@@ -41,6 +43,11 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -59,7 +66,7 @@ struct AttnParams {
 };
 
 template <int LP>
-__global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(LP * 2, LP == 128 ? 2 : (LP == 64 ? 7 : 12)) attn_kernel(const AttnParams p) {
     constexpr int NT = LP / 8;  // key tiles of 8
     extern __shared__ __align__(128) uint8_t attn_smem[];
     uint8_t* sq = attn_smem;
@@ -73,23 +80,31 @@ __global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
     const __nv_bfloat16* base = p.qkv + size_t(b) * L * 3 * D + h * DH;
 
     pdl_wait();
-    for (int i = tid; i < LP * 8 * 3; i += LP * 2) {
-        const int part = i / (LP * 8), rem = i % (LP * 8), r = rem >> 3, c = rem & 7;
-        uint8_t* dst = (part == 0 ? sq : part == 1 ? sk : sv) + tile_off(r, c);
-        const bool valid = r < L;
-        cp_async16(dst, base + size_t(valid ? r : 0) * 3 * D + part * D + c * 8, valid);
+    // Q and K first (one cp.async group), V second: S = Q.K^T and the softmax run while V is still in flight
+#pragma unroll
+    for (int part = 0; part < 3; ++part) {
+        uint8_t* dstp = part == 0 ? sq : part == 1 ? sk : sv;
+        for (int i = tid; i < LP * 8; i += LP * 2) {
+            const int r = i >> 3, c = i & 7;
+            const bool valid = r < L;
+            cp_async16(dstp + tile_off(r, c), base + size_t(valid ? r : 0) * 3 * D + part * D + c * 8, valid);
+        }
+        if (part >= 1) cp_async_commit();
     }
     for (int j = tid; j < LP; j += LP * 2) spad[j] = (j >= L) || (p.pad && p.pad[size_t(b) * L + j]);
-    cp_async_wait_all();
+    cp_async_wait_group<1>();
     __syncthreads();
     pdl_launch_dependents();
-    if (warp * 16 >= L) return;  // no valid query row in this warp (block-level syncs are all behind us)
+    const bool active = warp * 16 < L;  // warps without a valid query row only take part in the barriers
 
     // ---- S = Q K^T -------------------------------------------------------------------------------------
     float s[NT][4];
+    float inv0 = 0.f, inv1 = 0.f;
+    const int r0 = warp * 16 + (lane >> 2), r1 = r0 + 8;
+    const uint32_t q_base = smem_u32(sq), k_base = smem_u32(sk), v_base = smem_u32(sv);
+    if (active) {
 #pragma unroll
     for (int n = 0; n < NT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-    const uint32_t q_base = smem_u32(sq), k_base = smem_u32(sk), v_base = smem_u32(sv);
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) {
         uint32_t a0, a1, a2, a3;
@@ -104,17 +119,20 @@ __global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
     }
 
     // ---- masked softmax over keys (fp32; scale = 1/sqrt(64) folded into the exp2 argument) ---------------
-    const int r0 = warp * 16 + (lane >> 2), r1 = r0 + 8;
     const float kscale = 0.125f * 1.4426950408889634f;
+    // dead keys (padding, j >= L) as bit masks in registers: one shared-memory byte per lane instead of one per element
+    uint32_t dead[LP / 32];
+#pragma unroll
+    for (int w = 0; w < LP / 32; ++w) dead[w] = __ballot_sync(0xffffffffu, spad[w * 32 + lane] != 0);
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int j = n * 8 + (lane & 3) * 2 + e;
-            const bool dead = spad[j];
-            if (dead || (p.causal && j > r0)) s[n][e] = -INFINITY;
-            if (dead || (p.causal && j > r1)) s[n][2 + e] = -INFINITY;
+            const bool gone = (dead[(n * 8) / 32] >> (j & 31)) & 1u;
+            if (gone || (p.causal && j > r0)) s[n][e] = -INFINITY;
+            if (gone || (p.causal && j > r1)) s[n][2 + e] = -INFINITY;
             m0 = fmaxf(m0, s[n][e]);
             m1 = fmaxf(m1, s[n][2 + e]);
         }
@@ -123,13 +141,16 @@ __global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    // exp((s - m) / 8) = 2^(s*kscale - m*kscale): one FFMA + one MUFU.EX2 per element (a fully masked row keeps
+    // m = -inf and yields nan, like the reference's softmax)
+    const float mk0 = m0 * kscale, mk1 = m1 * kscale;
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            s[n][e] = exp2f((s[n][e] - m0) * kscale);
-            s[n][2 + e] = exp2f((s[n][2 + e] - m1) * kscale);
+            s[n][e] = ex2_approx(fmaf(s[n][e], kscale, -mk0));
+            s[n][2 + e] = ex2_approx(fmaf(s[n][2 + e], kscale, -mk1));
             sum0 += s[n][e];
             sum1 += s[n][2 + e];
         }
@@ -138,7 +159,7 @@ __global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;  // a fully masked row gives nan, like the reference
+    inv0 = 1.f / sum0, inv1 = 1.f / sum1;  // a fully masked row gives nan, like the reference
 
     if (p.probs) {  // need_weights row (model.py:265 CLS row, :381 EOS row) for the head average
         const int want = p.probs_row ? p.probs_row[b] : 0;
@@ -153,6 +174,11 @@ __global__ void __launch_bounds__(LP * 2) attn_kernel(const AttnParams p) {
             }
         }
     }
+
+    }  // active
+    cp_async_wait_group<0>();
+    __syncthreads();  // V has landed for every thread's copies
+    if (!active) return;
 
     // ---- O = P V ------------------------------------------------------------------------------------------
     float o[DH / 8][4];

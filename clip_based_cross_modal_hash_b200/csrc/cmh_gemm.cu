@@ -29,6 +29,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;              // two per TMEM lane quarter: they hide each other's TMEM / TMA-store latency
+constexpr int L2_PREFETCH_KB = 10;  // k-blocks between the L2 prefetch of a tile and its TMA load (ring depth + 4)
 constexpr int MMA_LOOKAHEAD = 2;  // k-blocks (of 4 MMAs) in flight in the tensor pipe
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1, TMEM_WARP = EPI_WARPS + 2;
 // The latency-critical single-thread roles get the HIGHEST warp ids: the SM's warp arbiter prefers higher ids, and with
@@ -88,6 +89,10 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
             smem_u32(smem_dst)),
         "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
+}
+// bring a tile into L2 ahead of its TMA load (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -296,8 +301,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sub = r & ((1 << p.tail_shift) - 1);
             width = BN >> p.tail_shift;
         }
-        m_idx = tile % p.tiles_m;
-        n_first = (tile / p.tiles_m) * BN + sub * width;
+        // column tiles fastest: the CTAs that run together share a few row blocks of A (the big operand: activations)
+        // and all of W, so A is read from HBM once — with row blocks fastest the K=3072 GEMM re-read the 79 MB
+        // activation matrix once per column tile and ran at HBM speed (profiles/README.md)
+        m_idx = tile / p.tiles_n;
+        n_first = (tile % p.tiles_n) * BN + sub * width;
     };
 
     if (warp == PRODUCER_WARP && lane == 0) {
@@ -338,6 +346,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&empty[stage], phase ^ 1u);
                 if (elect_one()) {
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                    if (kb + L2_PREFETCH_KB < kblocks) {  // hide the HBM part of the load latency behind the ring
+                        tma_prefetch_l2_2d(&tmA, (kb + L2_PREFETCH_KB) * BK, m0);
+                        tma_prefetch_l2_2d(mapB, (kb + L2_PREFETCH_KB) * BK, n0);
+                    }
                     if (CG == 1) {
                         mbar_arrive_expect_tx(&full[stage], stage_tx);
                         tma_load_2d(sa, &tmA, kb * BK, m0, &full[stage]);
