@@ -215,6 +215,31 @@ def calc_map_k(qB, rB, query_L, retrieval_L, k=None, *, mode: Optional[str] = No
         return result if isinstance(result, torch.Tensor) else torch.tensor(float(result), dtype=torch.float32)
 
 
+def calc_map_k_packed(q_codes, r_codes, query_L, retrieval_L, nbits: int, k=None):
+    """``calc_map_k`` on codes that are already bit-packed on the GPU (``models.get_code`` / ``encode_*_packed``:
+    int32 ``[n, W]``, bit b of word w = code column 32w+b).  Labels as in the reference (multi-hot ``[n, C]``, any
+    device).  Returns the same 0-dim fp32 CPU tensor as ``calc_map_k`` — no +-1 fp32 buffers, no device->host hop of
+    the codes (the reference forces them to the CPU at common/calc_utils.py:62-64)."""
+    dev = q_codes.device
+    if not (q_codes.is_cuda and r_codes.is_cuda):
+        raise CmhError("packed codes must live on the GPU")
+    ncls = retrieval_L.shape[1]
+    if nbits > 128 or ncls > 128:
+        raise CmhError("calc_map_k supports up to 128 bits and 128 classes (got %d, %d)" % (nbits, ncls))
+    if q_codes.shape[1] != R.code_words(nbits) or r_codes.shape[1] != R.code_words(nbits):
+        raise CmhError("packed codes must have %d words per row for %d bits" % (R.code_words(nbits), nbits))
+    k = retrieval_L.shape[0] if k is None else k
+    with torch.cuda.device(dev):
+        bad = R.new_bad_counter(dev)
+        qlp = R.pack_labels(_to_dev(query_L.detach(), dev), bad)
+        glp = R.pack_labels(_to_dev(retrieval_L.detach(), dev), bad)
+        res = R.map_k(q_codes.contiguous(), qlp, r_codes.contiguous(), glp, nbits, ncls, k)
+        host = torch.stack([res.map, bad[0].to(torch.float64)]).cpu()
+    if host[1] != 0:
+        raise ValueError("calc_map_k_packed: labels must be 0/1 (%d offending elements)" % int(host[1]))
+    return host[0].to(torch.float32)
+
+
 def hamming_topk(qB, rB, k: int):
     """First ``k`` columns of ``torch.sort(calc_hammingDist(qB, rB), stable=True)`` (calc_utils.py:76-77)
     -> ``(dist [Q,k] fp32, index [Q,k] int64)`` on the inputs' device (north_star's "per-query top-k")."""

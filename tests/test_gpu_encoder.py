@@ -218,6 +218,32 @@ def test_get_code_matches_batchwise_encoding():
         assert torch.equal(txt_codes[index.cuda()], model.encode_text_packed(text))
 
 
+def test_encode_to_map_pipeline_matches_float_path():
+    """get_code (packed) -> calc_map_k_packed == reference-shaped path: float head outputs -> make_hash_code -> calc_map_k."""
+    from clip_based_cross_modal_hash_b200 import calc_utils
+
+    nbits, B, nb, C = 32, 16, 4, 10
+    sd = synth.clip_state_dict(synth.TINY, seed=12)
+    model = models.DSPH(sd, synth.dsph_head_state_dict(synth.TINY["embed_dim"], nbits, seed=13))
+    loader, img_f, txt_f = [], [], []
+    for i in range(nb):
+        text, pad = synth.random_captions(B, seed=60 + i, vocab=synth.TINY["vocab_size"])
+        image = synth.random_images(B, seed=50 + i)
+        loader.append((image, text, pad, None, torch.arange(B) + i * B))
+        hi, ht = model(image, text)
+        img_f.append(model.make_hash_code(hi.clone()))
+        txt_f.append(model.make_hash_code(ht.clone()))
+    img_codes, txt_codes = models.get_code(model, loader, B * nb)
+    labels = synth.random_labels(B * nb, C, seed=70)
+    img_f, txt_f = torch.cat(img_f), torch.cat(txt_f)
+    assert bool((img_f.abs() == 1).all()), "a tanh output was exactly 0"
+    q = slice(0, B)   # first batch queries the whole set
+    want = calc_utils.calc_map_k(img_f[q], txt_f, labels[q], labels, 20)
+    got = calc_utils.calc_map_k_packed(img_codes[q], txt_codes, labels[q], labels, nbits, 20)
+    assert got.dtype == torch.float32 and got.device.type == "cpu"
+    assert float(got) == float(want)
+
+
 def test_encoder_rejects_bad_arguments():
     sd = synth.clip_state_dict(synth.TINY, seed=1)
     bb = encoder.ClipBackbone(sd)
