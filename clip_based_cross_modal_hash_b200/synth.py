@@ -157,3 +157,53 @@ def random_captions(batch: int, seed: int, max_words: int = 32, vocab: int = 494
         text[b, 1:e] = words[b, 1:e]
         text[b, e] = eot
     return text, text == 0
+
+
+def mith_head_state_dict(dim: int, nbits: int, seed: int = 0, layers: int = 2, res_mlp_layers: int = 2) -> dict:
+    """Keys of models/MITH/hash/hash.py HashLayer (gcl_i == gcl_t shared, lct_i / lct_t with a `layers`-block Transformer,
+    per-bit Linear(dim, 1) hashing, sin-cos `position.pe` buffer [nbits, 1, dim], concept projections)."""
+    import math
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    for i in range(res_mlp_layers):
+        sd["gcl_i.mlp.mlps.%d.0.weight" % i] = _normal(g, (4 * dim, dim), dim ** -0.5)
+        sd["gcl_i.mlp.mlps.%d.0.bias" % i] = _normal(g, (4 * dim,), 0.02)
+        sd["gcl_i.mlp.mlps.%d.3.weight" % i] = _normal(g, (dim, 4 * dim), (4 * dim) ** -0.5)
+        sd["gcl_i.mlp.mlps.%d.3.bias" % i] = _normal(g, (dim,), 0.02)
+    for i in range(res_mlp_layers):
+        sd["gcl_i.mlp.lns.%d.weight" % i] = 1 + _normal(g, (dim,), 0.05)
+        sd["gcl_i.mlp.lns.%d.bias" % i] = _normal(g, (dim,), 0.05)
+    sd["gcl_i.common_concept_embedding.weight"] = _normal(g, (nbits, dim), 2 * dim ** -0.5)
+    for k in [k for k in sd if k.startswith("gcl_i.")]:
+        sd["gcl_t." + k[6:]] = sd[k].clone()                       # one shared module in the reference (hash.py:217-218)
+    pe = torch.zeros(nbits, dim)
+    position = torch.arange(0, nbits, dtype=torch.float).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, dim, 2).float() * (-math.log(10000.0) / dim))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    pe = (pe / dim ** 0.5).unsqueeze(1)
+    for t in ("lct_i.", "lct_t."):
+        sd[t + "position.pe"] = pe.clone()
+        proj_std, attn_std, fc_std = (dim ** -0.5) * ((2 * layers) ** -0.5), dim ** -0.5, (2 * dim) ** -0.5
+        for i in range(layers):
+            p = "%stransformer.resblocks.%d." % (t, i)
+            sd[p + "attn.in_proj_weight"] = _normal(g, (3 * dim, dim), attn_std)
+            sd[p + "attn.in_proj_bias"] = _normal(g, (3 * dim,), 0.02)
+            sd[p + "attn.out_proj.weight"] = _normal(g, (dim, dim), proj_std)
+            sd[p + "attn.out_proj.bias"] = _normal(g, (dim,), 0.02)
+            sd[p + "ln_1.weight"] = 1 + _normal(g, (dim,), 0.05)
+            sd[p + "ln_1.bias"] = _normal(g, (dim,), 0.05)
+            sd[p + "mlp.c_fc.weight"] = _normal(g, (4 * dim, dim), fc_std)
+            sd[p + "mlp.c_fc.bias"] = _normal(g, (4 * dim,), 0.02)
+            sd[p + "mlp.c_proj.weight"] = _normal(g, (dim, 4 * dim), proj_std)
+            sd[p + "mlp.c_proj.bias"] = _normal(g, (dim,), 0.02)
+            sd[p + "ln_2.weight"] = 1 + _normal(g, (dim,), 0.05)
+            sd[p + "ln_2.bias"] = _normal(g, (dim,), 0.05)
+        for k in range(nbits):
+            sd["%shashing.fc_list.%d.weight" % (t, k)] = _normal(g, (1, dim), dim ** -0.5)
+            sd["%shashing.fc_list.%d.bias" % (t, k)] = _normal(g, (1,), 0.05)
+    for m in ("img", "txt"):
+        sd["%s_concept_proj.weight" % m] = _normal(g, (dim, dim), dim ** -0.5)
+        sd["%s_concept_proj.bias" % m] = _normal(g, (dim,), 0.02)
+    return sd
