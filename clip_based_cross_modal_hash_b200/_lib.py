@@ -113,8 +113,11 @@ PROTOTYPES = {
     "cmh_linear_f32": [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp],
     "cmh_head_dsph": [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "cmh_head_dcmht": [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp],
+    "cmh_head_mith_workspace_bytes": [_vp, _i64, _i32],
+    "cmh_head_mith": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp],
 }
-_RESTYPES = {"cmh_last_error": ctypes.c_char_p, "cmh_encoder_workspace_bytes": ctypes.c_int64}
+_RESTYPES = {"cmh_last_error": ctypes.c_char_p, "cmh_encoder_workspace_bytes": ctypes.c_int64,
+             "cmh_head_mith_workspace_bytes": ctypes.c_int64}
 
 _lib: Optional[ctypes.CDLL] = None
 

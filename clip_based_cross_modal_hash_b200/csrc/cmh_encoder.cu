@@ -101,10 +101,102 @@ int project(const cmh_tower* t, const Workspace& w, int64_t B, int L, const int3
     return gemm_bf16(w.att, B, D, D, t->w_out_proj, E, D, nullptr, CMH_EPI_F32, one_out, E, nullptr, 0, st);
 }
 
+// ---- MITH head -------------------------------------------------------------------------------------------------
+struct MithWs {
+    float *xc, *xt, *concept, *projout;
+    void *hc, *gc, *ht, *gt, *x2b;
+    void* tw;  // transformer workspace (carve)
+    int64_t tw_bytes, bytes;
+};
+
+MithWs carve_mith(const cmh_mith_head* h, int64_t B, int L, void* base) {
+    const int64_t D = h->dim, K = h->nbits, M = B * L, M2 = B * K;
+    MithWs w{};
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        void* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    w.xc = static_cast<float*>(take(B * D * 4));
+    w.hc = take(B * D * 2);
+    w.gc = take(B * 4 * D * 2);
+    w.xt = static_cast<float*>(take(M * D * 4));
+    w.ht = take(M * D * 2);
+    w.gt = take(M * 4 * D * 2);
+    w.concept = static_cast<float*>(take(M * K * 4));
+    w.x2b = take(M2 * D * 2);
+    w.projout = static_cast<float*>(take(M2 * D * 4));
+    w.tw_bytes = carve(&h->transformer, B, int(K), nullptr).bytes;
+    w.tw = take(w.tw_bytes);
+    w.bytes = off;
+    return w;
+}
+
+// ResidualMLPs.forward (hash.py:34-37) on `rows` rows of the fp32 stream x, in place
+int res_mlps(const cmh_mith_head* h, float* x, void* hb, void* gb, int64_t rows, cudaStream_t st) {
+    const int64_t D = h->dim;
+    for (int i = 0; i < h->mlp_layers; ++i) {
+        CMH_REQUIRE(h->w1[i] && h->w2[i] && h->ln_gain[i] && h->ln_bias[i], "mith: residual MLP %d has null weights", i);
+        if (int rc = layernorm(x, rows, int(D), 1, nullptr, h->ln_gain[i], h->ln_bias[i], LN_EPS, hb, false, st)) return rc;
+        if (int rc = gemm_bf16(hb, rows, D, D, h->w1[i], 4 * D, D, h->b1[i], CMH_EPI_ERF_GELU_BF16, gb, 4 * D, nullptr, 0, st)) return rc;
+        if (int rc = gemm_bf16(gb, rows, 4 * D, 4 * D, h->w2[i], D, 4 * D, h->b2[i], CMH_EPI_RESID_F32, x, D, x, D, st)) return rc;
+    }
+    return CMH_OK;
+}
+
 }  // namespace
 }  // namespace cmh
 
 extern "C" {
+
+int64_t cmh_head_mith_workspace_bytes(const cmh_mith_head* head, int64_t batch, int32_t tokens) {
+    if (!head || batch <= 0 || tokens <= 0 || head->nbits <= 0 || head->dim <= 0 || !head->transformer.blocks) return 0;
+    return cmh::carve_mith(head, batch, tokens, nullptr).bytes;
+}
+
+int cmh_head_mith(const cmh_mith_head* h, const float* cls, const float* tokens, int32_t per_sample, int32_t first, int32_t L,
+                  const uint8_t* pad, int64_t B, void* workspace, size_t workspace_bytes, float* res_cls, float* cls_hash,
+                  float* tokens_hash, float* trans_tokens, uint32_t* packed, void* stream) {
+    using namespace cmh;
+    CMH_REQUIRE(h && cls && tokens && cls_hash && tokens_hash && B > 0 && L > 0 && first >= 0 && first + L <= per_sample,
+                "head_mith: bad arguments");
+    CMH_REQUIRE(h->dim % 128 == 0 && h->nbits >= 1 && h->nbits <= 128 && h->mlp_layers >= 0 && h->mlp_layers <= CMH_MITH_MAX_MLP_LAYERS,
+                "head_mith: dim %d / k_bits %d / res_mlp_layers %d unsupported", h->dim, h->nbits, h->mlp_layers);
+    CMH_REQUIRE(h->w_concept && h->pos && h->w_bits && h->b_bits, "head_mith: missing weights");
+    CMH_REQUIRE(h->transformer.width == h->dim && h->transformer.heads * 64 == h->dim && h->transformer.blocks && h->transformer.layers > 0,
+                "head_mith: the concept transformer must have the head's width");
+    const int64_t D = h->dim, K = h->nbits;
+    const MithWs w = carve_mith(h, B, L, workspace);
+    if (!workspace || int64_t(workspace_bytes) < w.bytes || (reinterpret_cast<uintptr_t>(workspace) & 255))
+        return fail(CMH_ERR_WORKSPACE, "head_mith: workspace needs %lld bytes, 256-byte aligned", (long long)w.bytes);
+    cudaStream_t st = as_stream(stream);
+    // global branch: res_cls, cls_hash = gcl(cls)   (hash.py:233-234, 98-106)
+    if (int rc = gather_rows(cls, w.xc, B, 1, 1, 0, int(D), st)) return rc;
+    if (int rc = res_mlps(h, w.xc, w.hc, w.gc, B, st)) return rc;
+    if (int rc = linear_f32(w.xc, B, int(D), h->w_concept, nullptr, int(K), nullptr, nullptr, CMH_ACT_TANH, cls_hash, K, st)) return rc;
+    if (res_cls) {
+        if (int rc = normalize_rows(w.xc, B, int(D), res_cls, st)) return rc;
+    }
+    // local branch: concept embedding of every token (hash.py:235), aggregation to K concept tokens (+ position)
+    if (int rc = gather_rows(tokens, w.xt, B, L, per_sample, first, int(D), st)) return rc;
+    if (int rc = res_mlps(h, w.xt, w.ht, w.gt, B * L, st)) return rc;
+    if (int rc = linear_f32(w.xt, B * L, int(D), h->w_concept, nullptr, int(K), nullptr, nullptr, CMH_ACT_TANH, w.concept, K, st)) return rc;
+    const Workspace tw = carve(&h->transformer, B, int(K), w.tw);
+    if (int rc = token_aggregation(w.concept, tokens, pad, h->pos, B, L, int(K), int(D), per_sample, first, h->top_k, tw.x, st)) return rc;
+    // Transformer over the K concept tokens (hash.py:184-190), no mask
+    if (int rc = run_blocks(&h->transformer, tw, B, int(K), nullptr, 0, false, nullptr, st)) return rc;
+    // BitwiseHashing (hash.py:67-83)
+    if (int rc = bit_hash(tw.x, h->w_bits, h->b_bits, B * K, int(K), int(D), tokens_hash, st)) return rc;
+    if (trans_tokens) {  // normalize(concept_proj(x)) (hash.py:236, 244)
+        CMH_REQUIRE(h->w_cproj, "head_mith: trans_tokens requested without the concept projection weights");
+        if (int rc = cast_bf16(tw.x, w.x2b, B * K * D, st)) return rc;
+        if (int rc = gemm_bf16(w.x2b, B * K, D, D, h->w_cproj, D, D, h->b_cproj, CMH_EPI_F32, w.projout, D, nullptr, 0, st)) return rc;
+        if (int rc = normalize_rows(w.projout, B * K, int(D), trans_tokens, st)) return rc;
+    }
+    if (packed) return add_sign_pack(cls_hash, tokens_hash, B, int(K), packed, st);
+    return CMH_OK;
+}
 
 int64_t cmh_encoder_workspace_bytes(const cmh_tower* tower, int64_t batch, int32_t seq_len) {
     if (!tower || batch <= 0 || seq_len <= 0) return 0;

@@ -30,4 +30,13 @@ int attention_mean(const float* probs, int64_t B, int H, int L, int skip, const 
 int linear_f32(const float* x, int64_t rows, int K, const float* W, const float* bias, int N, const float* scale,
                const float* shift, int act, float* out, int64_t ldo, cudaStream_t st);
 int pair_softmax_pack(const float* logits, int64_t rows, int nbits, float* probs, uint32_t* packed, cudaStream_t st);
+
+// cmh_mith.cu
+int gather_rows(const float* src, float* dst, int64_t B, int L, int per_sample, int first, int D, cudaStream_t st);
+int token_aggregation(const float* concept, const float* x, const uint8_t* pad, const float* pos, int64_t B, int L, int K, int D,
+                      int per_sample, int first, int top_k, float* out, cudaStream_t st);
+int bit_hash(const float* x, const float* w, const float* bias, int64_t rows, int K, int D, float* out, cudaStream_t st);
+int normalize_rows(const float* x, int64_t rows, int D, float* out, cudaStream_t st);
+int cast_bf16(const float* x, void* out, int64_t n, cudaStream_t st);
+int add_sign_pack(const float* a, const float* b, int64_t rows, int nbits, uint32_t* packed, cudaStream_t st);
 }  // namespace cmh

@@ -413,7 +413,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // (+bias, activation) -> swizzled shared staging -> one TMA tile store (or fp32 reduce-add into the residual
         // stream); staging is double buffered per warp, stores are asynchronous and fully coalesced.
         const int e = warp, q = warp & 3, half = e >> 2;
-        const bool out_bf16 = p.epi == CMH_EPI_BF16 || p.epi == CMH_EPI_GELU_BF16;
+        const bool out_bf16 = p.epi == CMH_EPI_BF16 || p.epi == CMH_EPI_GELU_BF16 || p.epi == CMH_EPI_ERF_GELU_BF16;
         const int cw = out_bf16 ? 64 : 32;  // columns per chunk
         const uint32_t buf = smem_u32(stg_all + e * STG_WARP_BYTES);
         const uint32_t rowp = buf + lane * 128;
@@ -458,6 +458,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (p.epi == CMH_EPI_GELU_BF16) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+                        } else if (p.epi == CMH_EPI_ERF_GELU_BF16) {  // nn.GELU() of the MITH residual MLPs (hash.py:22)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
                         }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) pk[hh * 16 + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
@@ -585,7 +588,7 @@ int launch_gemm(const CUtensorMap& ta, const void* W, int64_t ldw, const CUtenso
     if (g_force_units > 0 && g_force_units < units) units = g_force_units;
     // Tail slicing: the R tiles of the last partial wave become R * 2^shift column slices on as many units.  A slice is
     // at least one epilogue chunk wide (64 bf16 / 32 fp32 columns) and the slices must fit one wave.
-    const bool out_bf16 = p.epi == CMH_EPI_BF16 || p.epi == CMH_EPI_GELU_BF16;
+    const bool out_bf16 = p.epi == CMH_EPI_BF16 || p.epi == CMH_EPI_GELU_BF16 || p.epi == CMH_EPI_ERF_GELU_BF16;
     const int rem = tiles % units;
     int shift = 0;
     if (g_tail_slicing && tiles > units && rem > 0) {
@@ -630,11 +633,11 @@ int gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, i
     CMH_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "gemm: bad arguments");
     CMH_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "gemm: leading dimensions must be multiples of 8 elements");
     CMH_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemm: operands must be 16-byte aligned");
-    CMH_REQUIRE(epi >= CMH_EPI_BF16 && epi <= CMH_EPI_TANH_F32, "gemm: unknown epilogue %d", epi);
-    CMH_REQUIRE(N % ((epi == CMH_EPI_BF16 || epi == CMH_EPI_GELU_BF16) ? 8 : 4) == 0,
+    CMH_REQUIRE(epi >= CMH_EPI_BF16 && epi <= CMH_EPI_ERF_GELU_BF16, "gemm: unknown epilogue %d", epi);
+    CMH_REQUIRE(N % ((epi == CMH_EPI_BF16 || epi == CMH_EPI_GELU_BF16 || epi == CMH_EPI_ERF_GELU_BF16) ? 8 : 4) == 0,
                 "gemm: N = %lld must be a multiple of the 16-byte output vector", (long long)N);
     CMH_REQUIRE(epi != CMH_EPI_RESID_F32 || resid, "gemm: residual epilogue needs resid");
-    const bool out_bf16 = epi == CMH_EPI_BF16 || epi == CMH_EPI_GELU_BF16;
+    const bool out_bf16 = epi == CMH_EPI_BF16 || epi == CMH_EPI_GELU_BF16 || epi == CMH_EPI_ERF_GELU_BF16;
     CMH_REQUIRE(ldo % (out_bf16 ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: output must be 16-byte aligned per row");
     CMH_REQUIRE(epi != CMH_EPI_RESID_F32 || (resid == out && ldr == ldo),
                 "gemm: the residual epilogue works in place (resid == out): it is a TMA fp32 reduce-add into the stream");

@@ -154,7 +154,8 @@ class ClipBackbone(torch.nn.Module):
         return torch.float32   # what callers feed (`image.type(self.dtype)`, model.py:366-371); arithmetic is bf16/fp32
 
     # ---- the two encoders ------------------------------------------------------------------------------------------
-    def encode_image(self, image: torch.Tensor):
+    def encode_image_raw(self, image: torch.Tensor, want_tokens: bool, want_attn: bool):
+        """-> (cls [B, E], tokens [B, L, E] or None, attn [B, L-1] or None): the C ABI's own (sample-major) layouts."""
         tw = self.visual
         c = tw.c
         if image.dim() != 4 or image.shape[1] != 3 or image.shape[2] != c.resolution or image.shape[3] != c.resolution:
@@ -164,16 +165,21 @@ class ClipBackbone(torch.nn.Module):
         with torch.cuda.device(self.device_):
             ws = tw.workspace(B, L, self.device_)
             cls = torch.empty((B, E), dtype=torch.float32, device=self.device_)
-            tokens = torch.empty((B, L, E), dtype=torch.float32, device=self.device_) if self.return_patches else None
-            attn = torch.empty((B, L - 1), dtype=torch.float32, device=self.device_) if self.return_patches else None
+            tokens = torch.empty((B, L, E), dtype=torch.float32, device=self.device_) if want_tokens else None
+            attn = torch.empty((B, L - 1), dtype=torch.float32, device=self.device_) if want_attn else None
             _lib.check(_lib.lib().cmh_encode_image(
                 ctypes.byref(c), image.data_ptr(), B, ws.data_ptr(), ws.numel(), cls.data_ptr(),
                 None if tokens is None else tokens.data_ptr(), None if attn is None else attn.data_ptr(), _stream()))
+        return cls, tokens, attn
+
+    def encode_image(self, image: torch.Tensor):
+        cls, tokens, attn = self.encode_image_raw(image, self.return_patches, self.return_patches)
         if self.return_patches:   # model.py:262-267
             return cls, tokens[:, 1:].permute(1, 0, 2), attn
         return cls
 
-    def encode_text(self, text: torch.Tensor, key_padding_mask: Optional[torch.Tensor] = None):
+    def encode_text_raw(self, text: torch.Tensor, key_padding_mask: Optional[torch.Tensor], want_tokens: bool, want_attn: bool):
+        """-> (eos [B, E], tokens [B, L, E] | None, attn [B, L] | None, new_mask uint8 [B, L] | None)."""
         tw = self.text
         c = tw.c
         if text.dim() != 2:
@@ -188,14 +194,18 @@ class ClipBackbone(torch.nn.Module):
         with torch.cuda.device(self.device_):
             ws = tw.workspace(B, L, self.device_)
             eos = torch.empty((B, E), dtype=torch.float32, device=self.device_)
-            rp = self.return_patches
-            tokens = torch.empty((B, L, E), dtype=torch.float32, device=self.device_) if rp else None
-            attn = torch.empty((B, L), dtype=torch.float32, device=self.device_) if rp else None
-            newmask = torch.empty((B, L), dtype=torch.uint8, device=self.device_) if (rp and pad is not None) else None
+            tokens = torch.empty((B, L, E), dtype=torch.float32, device=self.device_) if want_tokens else None
+            attn = torch.empty((B, L), dtype=torch.float32, device=self.device_) if want_attn else None
+            newmask = torch.empty((B, L), dtype=torch.uint8, device=self.device_) if (want_tokens and pad is not None) else None
             _lib.check(_lib.lib().cmh_encode_text(
                 ctypes.byref(c), text.data_ptr(), None if pad is None else pad.data_ptr(), B, L, ws.data_ptr(), ws.numel(),
                 eos.data_ptr(), None if tokens is None else tokens.data_ptr(), None if attn is None else attn.data_ptr(),
                 None if newmask is None else newmask.data_ptr(), _stream()))
+        return eos, tokens, attn, newmask
+
+    def encode_text(self, text: torch.Tensor, key_padding_mask: Optional[torch.Tensor] = None):
+        rp = self.return_patches
+        eos, tokens, attn, newmask = self.encode_text_raw(text, key_padding_mask, rp, rp)
         if rp:   # model.py:394-395
             return eos, tokens.permute(1, 0, 2), attn, (None if newmask is None else newmask.bool())
         return eos

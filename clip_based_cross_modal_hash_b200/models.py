@@ -14,7 +14,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from .encoder import ClipBackbone, _stream
+from .encoder import BlockWeights, ClipBackbone, Tower, _stream
 
 
 class DcmhtHeadStruct(ctypes.Structure):
@@ -183,13 +183,185 @@ class DCMHT(_Model):
         return torch.where(pairs[..., 1] > pairs[..., 0], 1.0, -1.0)
 
 
-def get_code(model, data_loader, length: int, device=None):
+class MithHeadStruct(ctypes.Structure):
+    """Mirror of ``struct cmh_mith_head``."""
+
+    _P4 = ctypes.c_void_p * 4
+    _fields_ = [("dim", ctypes.c_int32), ("nbits", ctypes.c_int32), ("mlp_layers", ctypes.c_int32), ("top_k", ctypes.c_int32),
+                ("ln_gain", _P4), ("ln_bias", _P4), ("w1", _P4), ("b1", _P4), ("w2", _P4), ("b2", _P4),
+                ("w_concept", ctypes.c_void_p), ("pos", ctypes.c_void_p), ("transformer", Tower),
+                ("w_bits", ctypes.c_void_p), ("b_bits", ctypes.c_void_p), ("w_cproj", ctypes.c_void_p), ("b_cproj", ctypes.c_void_p)]
+
+
+class MithHashLayer(_HeadBase):
+    """models/MITH/hash/hash.py:193-254 ``HashLayer`` (evaluation mode): global concept learning on the CLS/EOS feature,
+    localized token aggregation + a small transformer + bitwise hashing on the token features."""
+
+    def __init__(self, state_dict, device, top_k_label: int = 8):
+        self.top_k = top_k_label
+        super().__init__(state_dict, device)
+
+    def refresh(self):
+        sd, self.keep, self.heads, self.blocks = self._sd, [], {}, {}
+
+        def f32(t):
+            t = self._dev(t)
+            self.keep.append(t)
+            return t.data_ptr()
+
+        def bf16(t):
+            t = t.detach().to(device=self.device_, dtype=torch.bfloat16).contiguous()
+            self.keep.append(t)
+            return t.data_ptr()
+
+        for m, g, t in (("img", "gcl_i.", "lct_i."), ("txt", "gcl_t.", "lct_t.")):
+            h = MithHeadStruct()
+            h.nbits, h.dim = sd[g + "common_concept_embedding.weight"].shape
+            h.top_k = self.top_k
+            n = 0
+            while (g + "mlp.mlps.%d.0.weight" % n) in sd:
+                h.ln_gain[n], h.ln_bias[n] = f32(sd[g + "mlp.lns.%d.weight" % n]), f32(sd[g + "mlp.lns.%d.bias" % n])
+                h.w1[n], h.b1[n] = bf16(sd[g + "mlp.mlps.%d.0.weight" % n]), f32(sd[g + "mlp.mlps.%d.0.bias" % n])
+                h.w2[n], h.b2[n] = bf16(sd[g + "mlp.mlps.%d.3.weight" % n]), f32(sd[g + "mlp.mlps.%d.3.bias" % n])
+                n += 1
+            h.mlp_layers = n
+            h.w_concept = f32(sd[g + "common_concept_embedding.weight"])
+            h.pos = f32(sd[t + "position.pe"][: h.nbits, 0])
+            bp = t + "transformer.resblocks."
+            layers = len({k[len(bp):].split(".")[0] for k in sd if k.startswith(bp)})
+            blocks = (BlockWeights * layers)()
+            for i in range(layers):
+                p, b = "%s%d." % (bp, i), blocks[i]
+                b.ln1_gain, b.ln1_bias = f32(sd[p + "ln_1.weight"]), f32(sd[p + "ln_1.bias"])
+                b.w_qkv, b.b_qkv = bf16(sd[p + "attn.in_proj_weight"]), f32(sd[p + "attn.in_proj_bias"])
+                b.w_out, b.b_out = bf16(sd[p + "attn.out_proj.weight"]), f32(sd[p + "attn.out_proj.bias"])
+                b.ln2_gain, b.ln2_bias = f32(sd[p + "ln_2.weight"]), f32(sd[p + "ln_2.bias"])
+                b.w_fc, b.b_fc = bf16(sd[p + "mlp.c_fc.weight"]), f32(sd[p + "mlp.c_fc.bias"])
+                b.w_proj, b.b_proj = bf16(sd[p + "mlp.c_proj.weight"]), f32(sd[p + "mlp.c_proj.bias"])
+            self.blocks[m] = blocks
+            h.transformer.width, h.transformer.layers, h.transformer.heads = h.dim, layers, h.dim // 64
+            h.transformer.out_dim = h.dim
+            h.transformer.blocks = blocks
+            h.w_bits = f32(torch.stack([sd["%shashing.fc_list.%d.weight" % (t, k)][0] for k in range(h.nbits)]))
+            h.b_bits = f32(torch.stack([sd["%shashing.fc_list.%d.bias" % (t, k)][0] for k in range(h.nbits)]))
+            h.w_cproj, h.b_cproj = bf16(sd["%s_concept_proj.weight" % m]), f32(sd["%s_concept_proj.bias" % m])
+            self.heads[m] = h
+            self.nbits, self.in_dim = int(h.nbits), int(h.dim)
+        self._ws = None
+
+    def _run(self, m, cls, tokens, per_sample, first, L, pad, want_trans=True, packed=False):
+        """cls [B, D]; tokens: fp32 [*, D] buffer whose rows b*per_sample + first .. + L-1 are sample b's tokens."""
+        h = self.heads[m]
+        B, D, K = cls.shape[0], self.in_dim, self.nbits
+        dev = self.device_
+        need = _lib.lib().cmh_head_mith_workspace_bytes(ctypes.byref(h), B, L)
+        if need <= 0:
+            raise _lib.CmhError("cmh_head_mith_workspace_bytes failed")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        res = torch.empty((B, D), dtype=torch.float32, device=dev)
+        cls_hash = torch.empty((B, K), dtype=torch.float32, device=dev)
+        tok_hash = torch.empty((B, K), dtype=torch.float32, device=dev)
+        trans = torch.empty((B, K, D), dtype=torch.float32, device=dev) if want_trans else None
+        codes = torch.empty((B, _words(K)), dtype=torch.int32, device=dev) if packed else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cmh_head_mith(
+                ctypes.byref(h), cls.data_ptr(), tokens.data_ptr(), per_sample, first, L, None if pad is None else pad.data_ptr(), B,
+                self._ws.data_ptr(), self._ws.numel(), res.data_ptr(), cls_hash.data_ptr(), tok_hash.data_ptr(),
+                None if trans is None else trans.data_ptr(), None if codes is None else codes.data_ptr(), _stream()))
+        return res, cls_hash, tok_hash, trans, codes
+
+    @staticmethod
+    def _lnd_to_rows(tokens):
+        """The reference's [L, B, D] token layout -> contiguous sample-major rows [B*L, D]."""
+        return tokens.permute(1, 0, 2).contiguous()
+
+    def encode_img(self, img_cls, img_tokens):                                  # hash.py:231-238
+        cls, tok = self._feat(img_cls), self._lnd_to_rows(self._feat(img_tokens))
+        L = img_tokens.shape[0]
+        res, ch, th, trans, _ = self._run("img", cls, tok, L, 0, L, None)
+        return res, ch, th, trans.permute(1, 0, 2)
+
+    def encode_txt(self, txt_eos, txt_tokens, key_padding_mask):                # hash.py:240-247
+        cls, tok = self._feat(txt_eos), self._lnd_to_rows(self._feat(txt_tokens))
+        L = txt_tokens.shape[0]
+        pad = None if key_padding_mask is None else key_padding_mask.to(self.device_).to(torch.uint8).contiguous()
+        res, ch, th, trans, _ = self._run("txt", cls, tok, L, 0, L, pad)
+        return res, ch, th, trans.permute(1, 0, 2)
+
+    def forward(self, img_tokens, txt_tokens, img_cls, txt_eos, key_padding_mask):   # hash.py:249-254
+        return self.encode_img(img_cls, img_tokens) + self.encode_txt(txt_eos, txt_tokens, key_padding_mask)
+
+
+class MITH(torch.nn.Module):
+    """models/MITH/MITH.py (evaluation mode): backbone with ``return_patches=True`` + ``MithHashLayer``."""
+
+    def __init__(self, clip_state_dict, hash_state_dict, device="cuda", top_k_label: int = 8):
+        super().__init__()
+        self.backbone = ClipBackbone(clip_state_dict, return_patches=True, device=device)
+        self.hash = MithHashLayer(hash_state_dict, device, top_k_label)
+        self.output_dim = self.hash.nbits
+
+    def _image(self, image, want_trans, packed):
+        cls, tokens, _ = self.backbone.encode_image_raw(image, True, False)     # tokens [B, 50, E], row 0 = CLS
+        L = tokens.shape[1]
+        return self.hash._run("img", cls, tokens, L, 1, L - 1, None, want_trans, packed)
+
+    def _text(self, text, key_padding_mask, want_trans, packed):
+        eos, tokens, _, newmask = self.backbone.encode_text_raw(text, key_padding_mask, True, False)
+        L = tokens.shape[1]
+        return self.hash._run("txt", eos, tokens, L, 0, L, newmask, want_trans, packed)   # new mask: MITH.py:61-63
+
+    def encode_image(self, image):                                              # MITH.py:52-57
+        res, ch, th, trans, _ = self._image(image, True, False)
+        return res, ch, th, trans.permute(1, 0, 2)
+
+    def encode_text(self, text, key_padding_mask=None):                         # MITH.py:59-65
+        res, ch, th, trans, _ = self._text(text, key_padding_mask, True, False)
+        return res, ch, th, trans.permute(1, 0, 2)
+
+    def forward(self, image, text, key_padding_mask=None, labels=None, indexs=None, return_loss=False):   # MITH.py:67-76
+        if return_loss:
+            raise NotImplementedError("the training objective is outside the B200 hot path (DESIGN.md: out of scope)")
+        return self.encode_image(image) + self.encode_text(text, key_padding_mask)
+
+    def generate_hash(self, image, text, key_padding_mask=None):               # runners/MITH/runner.py:125-131
+        _, ich, ith, _, _ = self._image(image, False, False)
+        _, tch, tth, _, _ = self._text(text, key_padding_mask, False, False)
+        return ich + ith, tch + tth
+
+    @staticmethod
+    def make_hash_code(code):                                                   # runners/base.py:407-410
+        return code.sign_()
+
+    def encode_image_packed(self, image):
+        return self._image(image, False, True)[4]
+
+    def encode_text_packed(self, text, key_padding_mask=None):
+        return self._text(text, key_padding_mask, False, True)[4]
+
+
+def merge_code_buffers(*buffers, group=None):
+    """Combine per-rank packed code buffers under the reference's DDP evaluation pattern (runners/base.py:259-264): every rank
+    filled only the rows of its own sampler indices, the rest is zero.  One bitwise-OR all-reduce of the PACKED buffers
+    (COCO 64-bit gallery: 0.94 MB) replaces the reference's barrier + fp32 all-reduce(SUM) of [length, K] floats (30 MB) — and
+    rows that DistributedSampler duplicated to pad the last batch stay correct (the reference sums them to +-2)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for b in buffers:
+            dist.all_reduce(b, op=dist.ReduceOp.BOR, group=group)
+    return buffers
+
+
+def get_code(model, data_loader, length: int, device=None, distributed: bool = False, group=None):
     """Drop-in for ``BaseTrainer.get_code`` (runners/base.py:242-266) that stays bit-packed.
 
     ``data_loader`` yields the reference's batches ``(image, text, key_padding_mask, label, index)`` (host tensors,
     ideally pinned).  Returns ``(img_codes, txt_codes)``: int32 ``[length, W]`` device tensors in the evaluator's packed
-    layout, row ``index[i]`` of each buffer holding sample i's code — what ``calc_utils.calc_map_k`` consumes directly
-    (no +-1 fp32 ``[length, K]`` buffers, no device->host hop).  The host->device copy of batch i+1
+    layout, row ``index[i]`` of each buffer holding sample i's code — what ``calc_utils.calc_map_k_packed`` consumes directly
+    (no +-1 fp32 ``[length, K]`` buffers, no device->host hop).  ``distributed=True``: every rank encodes
+    its sampler's share and the buffers are merged by ``merge_code_buffers``.  The host->device copy of batch i+1
     runs on a side stream while batch i is encoded.
     """
     dev = torch.device(device) if device is not None else model.backbone.device_
@@ -199,22 +371,27 @@ def get_code(model, data_loader, length: int, device=None):
     main = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(dev)
 
+    needs_mask = isinstance(model, MITH)   # MITHTrainer.generate_hash passes key_padding_mask (runners/MITH/runner.py:125-131)
+
     def stage(batch):
-        image, text, _mask, _label, index = batch
+        image, text, mask, _label, index = batch
         with torch.cuda.stream(side):
-            item = (image.to(dev, non_blocking=True), text.to(dev, non_blocking=True),
-                    torch.as_tensor(index).to(dev, non_blocking=True).long())
+            item = [image.to(dev, non_blocking=True), text.to(dev, non_blocking=True),
+                    torch.as_tensor(index).to(dev, non_blocking=True).long()]
+            if needs_mask and mask is not None:
+                item.append(mask.to(dev, non_blocking=True))
             done = torch.cuda.Event()
             done.record(side)
         return item, done
 
     def encode(staged):
-        (image, text, index), done = staged
+        item, done = staged
         main.wait_event(done)
-        for t in (image, text, index):
+        for t in item:
             t.record_stream(main)
+        image, text, index = item[:3]
         img_buf[index] = model.encode_image_packed(image)
-        txt_buf[index] = model.encode_text_packed(text)
+        txt_buf[index] = model.encode_text_packed(text, item[3]) if len(item) > 3 else model.encode_text_packed(text)
 
     pending = None
     for batch in data_loader:
@@ -224,4 +401,6 @@ def get_code(model, data_loader, length: int, device=None):
         pending = nxt
     if pending is not None:
         encode(pending)
+    if distributed:
+        merge_code_buffers(img_buf, txt_buf, group=group)
     return img_buf, txt_buf

@@ -181,6 +181,7 @@ int cmh_euclid_sim_f32(const float* a, int64_t n, const float* b, int64_t m, int
 #define CMH_EPI_RESID_F32 2  /* out fp32 = resid + acc + bias      (residual stream)    */
 #define CMH_EPI_F32 3        /* out fp32 = acc + bias                                   */
 #define CMH_EPI_TANH_F32 4   /* out fp32 = tanh(acc + bias)        (DSPH head)          */
+#define CMH_EPI_ERF_GELU_BF16 5 /* out bf16 = GELU_erf(acc + bias) (MITH residual MLPs, models/MITH/hash/hash.py:22) */
 int cmh_gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, int64_t N, int64_t ldw,
                   const float* bias, int epilogue, void* out, int64_t ldo, const float* resid, int64_t ldr,
                   void* stream);
@@ -282,6 +283,39 @@ typedef struct cmh_dcmht_head {
  * runners/DCMHT/runner.py:83-95). */
 int cmh_head_dcmht(const float* feat, int64_t rows, int in_dim, const cmh_dcmht_head* head, int nbits, float* scratch,
                    float* probs, uint32_t* packed, void* stream);
+
+/* MITH head, eval mode (models/MITH/hash/hash.py:193-254), one modality (HashLayer.encode_img / encode_txt).
+ * Matrices of the residual MLPs, of the concept transformer and the concept projection are bf16 ([out][in]); the concept
+ * embedding, the per-bit hashing weights and every vector are fp32. */
+#define CMH_MITH_MAX_MLP_LAYERS 4
+typedef struct cmh_mith_head {
+    int32_t dim, nbits, mlp_layers, top_k;           /* 512, k_bits, res_mlp_layers, top_k_label                           */
+    const float* ln_gain[CMH_MITH_MAX_MLP_LAYERS];   /* gcl_*.mlp.lns.<i>.weight                                            */
+    const float* ln_bias[CMH_MITH_MAX_MLP_LAYERS];
+    const void*  w1[CMH_MITH_MAX_MLP_LAYERS];        /* gcl_*.mlp.mlps.<i>.0.weight [4D][D] bf16                            */
+    const float* b1[CMH_MITH_MAX_MLP_LAYERS];
+    const void*  w2[CMH_MITH_MAX_MLP_LAYERS];        /* gcl_*.mlp.mlps.<i>.3.weight [D][4D] bf16                            */
+    const float* b2[CMH_MITH_MAX_MLP_LAYERS];
+    const float* w_concept;                          /* gcl_*.common_concept_embedding.weight [K][D] fp32 (no bias)         */
+    const float* pos;                                /* lct_*.position.pe[:, 0, :] [K][D] fp32                              */
+    cmh_tower    transformer;                        /* lct_*.transformer: width, layers, heads, blocks (other fields unused) */
+    const float* w_bits; const float* b_bits;        /* lct_*.hashing.fc_list.<k>.weight stacked [K][D] / bias [K]          */
+    const void*  w_cproj; const float* b_cproj;      /* {img,txt}_concept_proj.weight [D][D] bf16 / bias                    */
+} cmh_mith_head;
+
+int64_t cmh_head_mith_workspace_bytes(const cmh_mith_head* head, int64_t batch, int32_t tokens);
+
+/* cls [B][D] fp32; the L tokens of sample b are rows b*tokens_per_sample + first_token .. +L-1 of `tokens` ([.][D] fp32:
+ * exactly the tokens_out buffer of cmh_encode_image (first_token = 1, L = 49) / cmh_encode_text (first_token = 0));
+ * key_padding_mask [B][L] uint8 or NULL (text: the new_mask_out of cmh_encode_text).
+ * Outputs fp32: res_cls [B][D] = normalize(mlp(cls)) (may be NULL), cls_hash [B][K], tokens_hash [B][K] (required),
+ * trans_tokens [B][K][D] = normalize(concept_proj(transformer tokens)) (may be NULL; the reference returns it as
+ * [K][B][D]); packed [B][W] (may be NULL) = bit-packed sign(cls_hash + tokens_hash)
+ * (MITHTrainer.generate_hash, runners/MITH/runner.py:125-131). */
+int cmh_head_mith(const cmh_mith_head* head, const float* cls, const float* tokens, int32_t tokens_per_sample,
+                  int32_t first_token, int32_t L, const uint8_t* key_padding_mask, int64_t batch, void* workspace,
+                  size_t workspace_bytes, float* res_cls, float* cls_hash, float* tokens_hash, float* trans_tokens,
+                  uint32_t* packed, void* stream);
 
 #ifdef __cplusplus
 }

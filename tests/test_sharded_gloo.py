@@ -69,3 +69,40 @@ def test_sharded_evaluator_over_gloo(tmp_path, world, name):
         idx = (o["keys"].numpy().view(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.int64)
         assert np.array_equal(idx, c.order_head[:, :50])
         assert torch.equal(o["keys"], outs[0]["keys"]) and o["map"] == outs[0]["map"]  # every rank agrees
+
+
+def _merge_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from clip_based_cross_modal_hash_b200 import models
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        full = torch.randint(-2 ** 31, 2 ** 31 - 1, (11, 2), generator=g, dtype=torch.int64).to(torch.int32)
+        # DistributedSampler pads 11 rows to 12 by repeating index 0: rank r owns indices r, r+world, ... of the padded list
+        padded = list(range(11)) + [0]
+        mine = padded[rank::world]
+        buf = torch.zeros_like(full)
+        buf[mine] = full[mine]
+        models.merge_code_buffers(buf)
+        out.put((rank, bool(torch.equal(buf, full))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_merge_code_buffers_bitwise_or_survives_sampler_padding():
+    """get_code's distributed merge: packed buffers, bitwise OR, duplicated (padded) rows stay exact."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    world, port = 2, 29653
+    procs = [ctx.Process(target=_merge_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
