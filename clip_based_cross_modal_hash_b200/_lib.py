@@ -89,6 +89,8 @@ PROTOTYPES = {
     "cmh_make_plan": [_i64, _i64, _i64, _i32, _i32, _i32, _PP],
     "cmh_hist": [_PP, _vp, _vp, _vp, _vp, _vp, _vp],
     "cmh_scan": [_PP, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "cmh_hist_totals": [_PP, _vp, _vp, _vp],
+    "cmh_scan_sharded": [_PP, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cmh_rank_map": [_PP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
     "cmh_map_finish": [_PP, _vp, _i32, _vp, _vp, _vp, _vp],
     "cmh_rank_topk": [_PP, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp],

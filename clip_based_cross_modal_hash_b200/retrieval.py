@@ -179,6 +179,35 @@ class CudaStages:
                                       o["thresh"].data_ptr(), _stream()))
         return o
 
+    def hist_totals(self, plan: Plan, hist: torch.Tensor) -> torch.Tensor:
+        """[nchunks, bins, Qpad] packed histogram block -> this rank's bucket totals int32 [2, bins, Qpad] (all, relevant)."""
+        dev = _need_cuda(hist)
+        totals = torch.empty((2, plan.bins, plan.Qpad), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_hist_totals(ctypes.byref(plan), hist.data_ptr(), totals.data_ptr(), _stream()))
+        return totals
+
+    def scan_sharded(self, plan: Plan, hist_local: torch.Tensor, totals_all: torch.Tensor, world: int, rank: int,
+                     k: Optional[int]) -> Dict[str, torch.Tensor]:
+        """``scan`` for one rank of a sharded gallery from its own histogram block and everyone's bucket totals."""
+        dev = _need_cuda(hist_local, totals_all)
+        shape = (plan.nchunks, plan.bins, plan.Qpad)
+        o = {
+            "within_all": torch.empty(shape, dtype=torch.int32, device=dev),
+            "below_all": torch.empty((plan.bins, plan.Qpad), dtype=torch.int32, device=dev),
+            "within_rel": torch.empty(shape, dtype=torch.int32, device=dev),
+            "below_rel": torch.empty((plan.bins, plan.Qpad), dtype=torch.int32, device=dev),
+            "tsum": torch.empty(plan.Qpad, dtype=torch.int32, device=dev),
+            "total": torch.empty(plan.Qpad, dtype=torch.int32, device=dev),
+            "thresh": torch.empty(plan.Qpad, dtype=torch.int32, device=dev),
+        }
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_scan_sharded(ctypes.byref(plan), hist_local.data_ptr(), totals_all.data_ptr(), world, rank,
+                                              int(k) if k else 0, o["within_all"].data_ptr(), o["within_rel"].data_ptr(),
+                                              o["below_all"].data_ptr(), o["below_rel"].data_ptr(), o["tsum"].data_ptr(),
+                                              o["total"].data_ptr(), o["thresh"].data_ptr(), _stream()))
+        return o
+
     def rank_map(self, plan: Plan, qp, qlp, gp, glp, sc: Dict[str, torch.Tensor],
                  tindex: Optional[torch.Tensor] = None, n_total: Optional[int] = None) -> torch.Tensor:
         dev = _need_cuda(qp, qlp, gp, glp, tindex)
@@ -314,7 +343,7 @@ class ShardedEvaluator:
     """mAP / top-k with the gallery sharded over ``group``; queries (and their labels) are replicated.
 
     Exchange steps (all ``all_gather_into_tensor``; NCCL over NVLink on GPUs, gloo in the CPU tests):
-      mAP    : per-shard histograms [nchunks, bins, Qpad] int32  ->  scan  ->  per-chunk AP partials fp64
+      mAP    : per-shard bucket totals [2, bins, Qpad] int32  ->  scan  ->  per-chunk AP partials fp64
       top-k  : per-shard partial top-k keys [Q, k] int64 (ONE all-gather) -> merge kernel
     Every rank ends with the identical result.
     """
@@ -348,8 +377,9 @@ class ShardedEvaluator:
         n_geom = self._geometry(n_local, n_geom, qp.device)
         plan = st.make_plan(Q, n_local, nbits, ncls, n_geom)
         hist = st.hist(plan, qp, qlp, gp_local, glp_local)
-        hist_all = self._gather(hist)                          # [world, nchunks, bins, Qpad]
-        sc = st.scan(plan, hist_all, self.world, self.rank, k)
+        # a rank's chunks follow all chunks of the lower ranks: only the per-bucket totals travel
+        totals_all = self._gather(st.hist_totals(plan, hist))  # [world, 2, bins, Qpad]
+        sc = st.scan_sharded(plan, hist, totals_all, self.world, self.rank, k)
         tindex = None
         if tindex_cap:
             tindex = torch.zeros((Q, tindex_cap), dtype=torch.int32, device=qp.device)

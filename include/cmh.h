@@ -117,6 +117,18 @@ int cmh_scan(const cmh_plan* plan, const uint32_t* hist_all, int world, int rank
              uint32_t* within_all, uint32_t* within_rel, uint32_t* below_all, uint32_t* below_rel,
              int32_t* tsum, int32_t* total, int32_t* thresh, void* stream);
 
+/* Sharded form of the same scan (what ShardedEvaluator.map_k uses): a rank's chunks follow every chunk of the lower ranks
+ * in gallery order, so the other ranks only have to contribute their per-bucket totals.
+ * cmh_hist_totals: totals[0][d][q] = #items of this rank at distance d, totals[1][d][q] = #relevant ones
+ *                  (uint32 [2][bins][Qpad]; summed over this rank's chunks).
+ * cmh_scan_sharded: hist_local = this rank's block [nchunks][bins][Qpad]; totals_all = the all-gathered totals
+ *                  [world][2][bins][Qpad].  Outputs as cmh_scan.  Exchange volume per rank: 2*bins*Qpad*4 bytes
+ *                  (C2: 2.6 MB) instead of nchunks*bins*Qpad*4 (C2: 78 MB). */
+int cmh_hist_totals(const cmh_plan* plan, const uint32_t* hist, uint32_t* totals, void* stream);
+int cmh_scan_sharded(const cmh_plan* plan, const uint32_t* hist_local, const uint32_t* totals_all, int world, int rank,
+                     int64_t k, uint32_t* within_all, uint32_t* within_rel, uint32_t* below_all, uint32_t* below_rel,
+                     int32_t* tsum, int32_t* total, int32_t* thresh, void* stream);
+
 /* ---- R4 pass 2 (mAP): ranks of the relevant items and their AP terms ----------------------------------
  * Replaces the per-query loop common/calc_utils.py:84-89.
  * ap_partial[c][q] = fp64 sum over this chunk's relevant items j with relevant-rank r_j < total[q] of

@@ -69,6 +69,36 @@ class OracleStages:
                 "below_all": t32(ba), "below_rel": t32(br) if with_rel else None,
                 "tsum": t32(tsum), "total": t32(total), "thresh": t32(thresh)}
 
+    def hist_totals(self, plan, hist):
+        h = _u32(hist).astype(np.int64)
+        return torch.from_numpy(np.stack([(h & 0xFFFF).sum(axis=0), (h >> 16).sum(axis=0)]).astype(np.int32))
+
+    def scan_sharded(self, plan, hist_local, totals_all, world, rank, k):
+        """Same contract as CudaStages.scan_sharded: rebuild the global view from the totals (every other rank's block is
+        replaced by one pseudo-chunk holding its totals — only sums over lower ranks and over all ranks are used)."""
+        h = _u32(hist_local).astype(np.int64)
+        ha, hr = h & 0xFFFF, h >> 16
+        t = totals_all.numpy().astype(np.int64)                 # [world, 2, bins, Qpad]
+        base_a, base_r = t[:rank, 0].sum(axis=0), t[:rank, 1].sum(axis=0)
+        wa = base_a[None] + np.cumsum(ha, axis=0) - ha
+        wr = base_r[None] + np.cumsum(hr, axis=0) - hr
+        ta, tr = t[:, 0].sum(axis=0), t[:, 1].sum(axis=0)
+        ba = np.cumsum(ta, axis=0) - ta
+        br = np.cumsum(tr, axis=0) - tr
+        tsum = tr.sum(axis=0)
+        kk = int(k) if k else 0
+        total = np.minimum(tsum, kk) if kk > 0 else tsum
+        cum = np.cumsum(ta, axis=0)
+        thresh = np.full(plan.Qpad, plan.bins - 1, dtype=np.int64)
+        if kk > 0:
+            for q in range(plan.Qpad):
+                hit = np.nonzero(cum[:, q] >= kk)[0]
+                if hit.size:
+                    thresh[q] = hit[0]
+        t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a).astype(np.int32))
+        return {"within_all": t32(wa), "within_rel": t32(wr), "below_all": t32(ba), "below_rel": t32(br),
+                "tsum": t32(tsum), "total": t32(total), "thresh": t32(thresh)}
+
     def _positions(self, drow, bins):
         """in-bucket position (index order) of every item of a chunk."""
         ranks = ho.stable_ranks(drow, bins)

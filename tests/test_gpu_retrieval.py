@@ -163,9 +163,14 @@ def test_sharded_stages_match_single(name, world):
     cap = max(int(c.totals.max()), 1)
     tindex = torch.zeros((c.Q, cap), dtype=torch.int32, device=DEV)
     parts = []
+    totals_all = torch.stack([st.hist_totals(p, h) for p, h in zip(plans, hists)])    # what the ranks all-gather
     for r, (p, (lo, hi)) in enumerate(zip(plans, bounds)):
         sc = st.scan(p, hist_all, world, r, c.k)
         assert np.array_equal(sc["total"][: c.Q].cpu().numpy(), c.totals)
+        # the reduced exchange (per-rank bucket totals only) gives bit-identical rank bases
+        sc2 = st.scan_sharded(p, hists[r], totals_all, world, r, c.k)
+        for key in ("within_all", "within_rel", "below_all", "below_rel", "tsum", "total", "thresh"):
+            assert torch.equal(sc[key], sc2[key]), key
         mine = torch.zeros_like(tindex)
         parts.append(st.rank_map(p, qp, qlp, gp[lo:hi], glp[lo:hi], sc, mine, n_total=c.N))
         assert not ((tindex != 0) & (mine != 0)).any()  # each slot owned by exactly one shard
