@@ -4,7 +4,7 @@
 // (:373-396).  Activations are token-major [B*L][D] (sample-major, so one sample's tokens are contiguous — the
 // reference permutes to [L][B][D] for nn.MultiheadAttention, :246,377):
 //
-//   x    fp32 [M][D]    residual stream; out_proj / c_proj add into it through the GEMM's TMA reduce-add epilogue
+//   x    fp32 [M][D]    residual stream; out_proj / c_proj add into it through the GEMM epilogue (vector red.add)
 //   h    bf16 [M][D]    LayerNorm output = A operand of the next GEMM
 //   qkv  bf16 [M][3D]   in_proj output;  att bf16 [M][D] attention output;  fc bf16 [M][4D] QuickGELU(c_fc)
 //

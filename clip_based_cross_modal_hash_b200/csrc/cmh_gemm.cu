@@ -5,17 +5,19 @@
 // replaces the fp32 cuBLAS SGEMMs behind nn.Linear / nn.MultiheadAttention / conv1 of models/CLIP/model.py:167-268.
 //
 // Persistent, warp-specialised, one CTA per SM.  CG = 2 pairs the two SMs of a TPC on one 256 x BN tile
-// (tcgen05.mma.cta_group::2): each CTA stages its own 128 rows of A and HALF of the W tile, so the bytes every SM pulls
-// from L2 per MAC drop by ~1.7x — the single-CTA kernel is bound by L2->SM bandwidth (~44 B/clk/SM), not by the tensor pipe.
-//   warp 8      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) of a 128 x 64 A tile and a BN x 64 W tile
-//                              into a 4..6-stage shared-memory ring, completion on mbarriers (expect_tx)
-//   warp 9      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x 4
-//                              per stage; tcgen05.commit releases the stage / publishes the accumulator
+// (tcgen05.mma.cta_group::2): each CTA stages its own 128 rows of A and HALF of the W tile (fewer bytes per MAC from L2
+// and half the shared-memory operand reads per SM).
+//   warps 0..7  epilogue       tcgen05.ld 32x32b.x32 -> registers -> bias (prefetched, one column per lane) / QuickGELU /
+//                              erf-GELU / tanh -> swizzled shared staging -> coalesced 16-byte global stores, or
+//                              red.global.add.v4.f32 into the fp32 residual stream
+//   warp 8      TMA producer   cp.async.bulk.tensor.2d (128B swizzle) of a 128 x 64 A tile and a (BN/CG) x 64 W tile into a
+//                              5..8-stage shared-memory ring, completion on mbarriers (expect_tx); L2 prefetch 10 k-blocks ahead
+//   warp 9      MMA issuer     warp-converged, elect.sync-predicated tcgen05.mma.kind::f16 (M=128*CG, N=BN, K=16) x 4 per
+//                              stage, at most 2 stages queued; tcgen05.commit releases the stage / publishes the accumulator
 //   warp 10     TMEM owner     tcgen05.alloc of 2 x BN fp32 accumulator columns (double buffered) / dealloc
-//   warps 0..7  epilogue       tcgen05.ld 32x32b.x32 -> registers -> bias / QuickGELU / tanh -> swizzled smem staging
-//                              -> TMA tile store (cp.async.bulk.tensor) or, for the residual stream, TMA fp32
-//                              reduce-add (cp.reduce.async.bulk.tensor .add) straight into x
-// The epilogue of tile i overlaps the MMAs of tile i+1 through the two TMEM accumulator stages.
+// The epilogue of tile i overlaps the MMAs of tile i+1 through the two TMEM accumulator stages; the tiles of the last,
+// partial wave are cut into column slices; every launch is a programmatic dependent launch (prologue overlaps the
+// previous kernel's tail).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -28,14 +30,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;              // two per TMEM lane quarter: they hide each other's TMEM / TMA-store latency
+constexpr int EPI_WARPS = 8;        // two per TMEM lane quarter: they hide each other's TMEM-load latency
 constexpr int L2_PREFETCH_KB = 10;  // k-blocks between the L2 prefetch of a tile and its TMA load (ring depth + 4)
 constexpr int MMA_LOOKAHEAD = 2;  // k-blocks (of 4 MMAs) in flight in the tensor pipe
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1, TMEM_WARP = EPI_WARPS + 2;
 // The latency-critical single-thread roles get the HIGHEST warp ids: the SM's warp arbiter prefers higher ids, and with
 // the epilogue warps above them the MMA issue loop lost ~20 % once an epilogue ran concurrently (profiles/README.md).
 constexpr int GEMM_THREADS = (EPI_WARPS + 3) * 32;
-constexpr int STG_CHUNK_BYTES = 4096;     // one epilogue chunk: 32 rows x 128 B (64 bf16 or 32 fp32 columns), SWIZZLE_128B
+constexpr int STG_CHUNK_BYTES = 4096;  // one epilogue chunk: 32 rows x 128 B (64 bf16 or 32 fp32 columns), XOR-swizzled
 // One staging buffer per warp.  The epilogue leaves through ordinary coalesced 16-byte stores / vector reductions, not TMA:
 // a TMA store queues behind the operand loads in the SM's TMA unit, and with a deep operand ring its shared-memory read
 // took ~2000 clk, which made the epilogue 3x slower than the main loop (profiles/README.md).
@@ -129,25 +131,9 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 // shared -> global tile store / fp32 reduce-add through the tensor map (clips rows/columns outside the tensor)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t smem_src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_src),
-                 "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int c0, int c1, uint32_t smem_src) {
-    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-                 "r"(smem_src), "r"(c0), "r"(c1)
-                 : "memory");
-}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -162,12 +148,6 @@ __device__ __forceinline__ void red_add_f32x4(void* gptr, uint4 v) {
                  "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
                  : "memory");
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 template <int CG>
@@ -273,7 +253,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
     using C = GemmCfg<BN, CG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -543,21 +523,6 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// output tile map: 32 rows x 128 bytes per store (64 bf16 or 32 fp32 columns), SWIZZLE_128B
-int make_out_tmap(CUtensorMap* map, void* base, int64_t rows, int64_t cols, int64_t ld, bool bf16) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return fail(CMH_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-    cuuint64_t strides[1] = {cuuint64_t(ld) * (bf16 ? 2 : 4)};
-    cuuint32_t box[2] = {cuuint32_t(bf16 ? 64 : 32), 32};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(CMH_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with CUresult %d", int(r));
-    return CMH_OK;
-}
-
 // 2-D bf16 tensor map: rows x cols (cols contiguous), box = box_rows x 64 columns, 128-byte swizzle
 int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     EncodeTiledFn fn = encode_fn();
@@ -574,7 +539,7 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
 }
 
 template <int BN, int CG>
-int launch_gemm(const CUtensorMap& ta, const void* W, int64_t ldw, const CUtensorMap& to, GemmParams p, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& ta, const void* W, int64_t ldw, GemmParams p, cudaStream_t st) {
     using C = GemmCfg<BN, CG>;
     static bool configured = false;
     if (!configured) {
@@ -605,7 +570,7 @@ int launch_gemm(const CUtensorMap& ta, const void* W, int64_t ldw, const CUtenso
     if (int rc = make_tmap(&tb2, W, p.N, p.K, ldw, (BN >> shift) / CG)) return rc;
     const int grid_units = p.num_items < units ? p.num_items : units;
     CMH_CUDA_TRY(launch_kernel(gemm_bf16_kernel<BN, CG>, dim3(unsigned(grid_units * CG)), dim3(GEMM_THREADS), C::SMEM_BYTES, st, CG,
-                               ta, tb, tb2, to, p));
+                               ta, tb, tb2, p));
     return CMH_OK;
 }
 
@@ -640,28 +605,27 @@ int gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, i
     const bool out_bf16 = epi == CMH_EPI_BF16 || epi == CMH_EPI_GELU_BF16 || epi == CMH_EPI_ERF_GELU_BF16;
     CMH_REQUIRE(ldo % (out_bf16 ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: output must be 16-byte aligned per row");
     CMH_REQUIRE(epi != CMH_EPI_RESID_F32 || (resid == out && ldr == ldo),
-                "gemm: the residual epilogue works in place (resid == out): it is a TMA fp32 reduce-add into the stream");
+                "gemm: the residual epilogue works in place (resid == out): it is a vector red.add into the stream");
     int bn = 128, cg = 1;
     pick_tile(M, N, &bn, &cg);
     if (g_force_bn > 0) bn = g_force_bn;
     if (g_force_cg > 0) cg = g_force_cg;
-    CUtensorMap ta, to;
+    CUtensorMap ta;
     if (int rc = make_tmap(&ta, A, M, K, lda, BM)) return rc;
-    if (int rc = make_out_tmap(&to, out, M, N, ldo, out_bf16)) return rc;
     GemmParams p{};
     p.M = M, p.N = N, p.K = K, p.bias = bias, p.out = out, p.ldo = ldo, p.resid = resid, p.ldr = ldr, p.epi = epi;
     p.trace = g_trace;
     if (cg == 2) {
         switch (bn) {
-            case 256: return launch_gemm<256, 2>(ta, W, ldw, to, p, st);
-            case 192: return launch_gemm<192, 2>(ta, W, ldw, to, p, st);
-            default: return launch_gemm<128, 2>(ta, W, ldw, to, p, st);
+            case 256: return launch_gemm<256, 2>(ta, W, ldw, p, st);
+            case 192: return launch_gemm<192, 2>(ta, W, ldw, p, st);
+            default: return launch_gemm<128, 2>(ta, W, ldw, p, st);
         }
     }
     switch (bn) {
-        case 256: return launch_gemm<256, 1>(ta, W, ldw, to, p, st);
-        case 192: return launch_gemm<192, 1>(ta, W, ldw, to, p, st);
-        default: return launch_gemm<128, 1>(ta, W, ldw, to, p, st);
+        case 256: return launch_gemm<256, 1>(ta, W, ldw, p, st);
+        case 192: return launch_gemm<192, 1>(ta, W, ldw, p, st);
+        default: return launch_gemm<128, 1>(ta, W, ldw, p, st);
     }
 }
 
