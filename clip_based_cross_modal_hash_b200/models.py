@@ -247,7 +247,7 @@ class MithHashLayer(_HeadBase):
             h.w_cproj, h.b_cproj = bf16(sd["%s_concept_proj.weight" % m]), f32(sd["%s_concept_proj.bias" % m])
             self.heads[m] = h
             self.nbits, self.in_dim = int(h.nbits), int(h.dim)
-        self._ws = None
+        self._ws = {}   # one workspace per modality: the two branches may run on different streams (get_code)
 
     def _run(self, m, cls, tokens, per_sample, first, L, pad, want_trans=True, packed=False):
         """cls [B, D]; tokens: fp32 [*, D] buffer whose rows b*per_sample + first .. + L-1 are sample b's tokens."""
@@ -257,8 +257,9 @@ class MithHashLayer(_HeadBase):
         need = _lib.lib().cmh_head_mith_workspace_bytes(ctypes.byref(h), B, L)
         if need <= 0:
             raise _lib.CmhError("cmh_head_mith_workspace_bytes failed")
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        ws = self._ws.get(m)
+        if ws is None or ws.numel() < need:
+            ws = self._ws[m] = torch.empty(need, dtype=torch.uint8, device=dev)
         res = torch.empty((B, D), dtype=torch.float32, device=dev)
         cls_hash = torch.empty((B, K), dtype=torch.float32, device=dev)
         tok_hash = torch.empty((B, K), dtype=torch.float32, device=dev)
@@ -267,7 +268,7 @@ class MithHashLayer(_HeadBase):
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().cmh_head_mith(
                 ctypes.byref(h), cls.data_ptr(), tokens.data_ptr(), per_sample, first, L, None if pad is None else pad.data_ptr(), B,
-                self._ws.data_ptr(), self._ws.numel(), res.data_ptr(), cls_hash.data_ptr(), tok_hash.data_ptr(),
+                ws.data_ptr(), ws.numel(), res.data_ptr(), cls_hash.data_ptr(), tok_hash.data_ptr(),
                 None if trans is None else trans.data_ptr(), None if codes is None else codes.data_ptr(), _stream()))
         return res, cls_hash, tok_hash, trans, codes
 
@@ -369,33 +370,57 @@ def get_code(model, data_loader, length: int, device=None, distributed: bool = F
     img_buf = torch.zeros((length, W), dtype=torch.int32, device=dev)
     txt_buf = torch.zeros((length, W), dtype=torch.int32, device=dev)
     main = torch.cuda.current_stream(dev)
-    side = torch.cuda.Stream(dev)
+    side = torch.cuda.Stream(dev)          # host -> device copies of the next batch
+    txt_stream = torch.cuda.Stream(dev)    # the text tower runs beside the image tower: each fills the other's partial waves
 
     needs_mask = isinstance(model, MITH)   # MITHTrainer.generate_hash passes key_padding_mask (runners/MITH/runner.py:125-131)
+    # two sets of device staging buffers (allocated from the first batch's shapes): no allocator traffic across streams
+    slots = [None, None]
+    free = [None, None]   # event: the batch that last used this slot has been encoded
 
-    def stage(batch):
+    def stage(batch, j):
         image, text, mask, _label, index = batch
+        index = torch.as_tensor(index)
+        n = image.shape[0]
+        if slots[j] is None or slots[j][0].shape[0] < n or slots[j][1].shape[1] != text.shape[1]:
+            slots[j] = [torch.empty((n,) + tuple(image.shape[1:]), dtype=torch.float32, device=dev),
+                        torch.empty((n, text.shape[1]), dtype=torch.int64, device=dev),
+                        torch.empty((n,), dtype=torch.int64, device=dev),
+                        torch.empty((n, text.shape[1]), dtype=torch.bool, device=dev)]
+            free[j] = None
+            torch.cuda.current_stream(dev).synchronize()   # (re)allocation only: first batches or a larger batch
+        if free[j] is not None:
+            side.wait_event(free[j])
         with torch.cuda.stream(side):
-            item = [image.to(dev, non_blocking=True), text.to(dev, non_blocking=True),
-                    torch.as_tensor(index).to(dev, non_blocking=True).long()]
-            if needs_mask and mask is not None:
-                item.append(mask.to(dev, non_blocking=True))
+            bufs = slots[j]
+            bufs[0][:n].copy_(image, non_blocking=True)
+            bufs[1][:n].copy_(text, non_blocking=True)
+            bufs[2][:n].copy_(index, non_blocking=True)
+            has_mask = needs_mask and mask is not None
+            if has_mask:
+                bufs[3][:n].copy_(mask, non_blocking=True)
             done = torch.cuda.Event()
             done.record(side)
-        return item, done
+        return (j, n, has_mask), done
 
     def encode(staged):
-        item, done = staged
+        (j, n, has_mask), done = staged
+        image, text, index, mask = (t[:n] for t in slots[j])
         main.wait_event(done)
-        for t in item:
-            t.record_stream(main)
-        image, text, index = item[:3]
-        img_buf[index] = model.encode_image_packed(image)
-        txt_buf[index] = model.encode_text_packed(text, item[3]) if len(item) > 3 else model.encode_text_packed(text)
+        txt_stream.wait_stream(main)       # orders the text tower after everything queued so far (inputs, txt_buf writes)
+        with torch.cuda.stream(txt_stream):
+            tcodes = model.encode_text_packed(text, mask) if has_mask else model.encode_text_packed(text)
+        icodes = model.encode_image_packed(image)
+        main.wait_stream(txt_stream)
+        tcodes.record_stream(main)
+        img_buf[index] = icodes
+        txt_buf[index] = tcodes
+        free[j] = torch.cuda.Event()
+        free[j].record(main)
 
     pending = None
-    for batch in data_loader:
-        nxt = stage(batch)
+    for i, batch in enumerate(data_loader):
+        nxt = stage(batch, i & 1)
         if pending is not None:
             encode(pending)
         pending = nxt

@@ -41,3 +41,19 @@ with torch.cuda.stream(s):
         out = bb.encode_image(img)
 ms = timeit(lambda: g.replay())
 print('encode_image (CUDA graph) B=%d: %.3f ms  %.0f img/s  %.0f TFLOP/s' % (B, ms, B / ms * 1e3, port.flops_image() * B / ms / 1e9))
+
+# image and text towers on two streams (do they fill each other's tails?)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+def both():
+    s1.wait_stream(torch.cuda.current_stream()); s2.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s1):
+        bb.encode_image(img)
+    with torch.cuda.stream(s2):
+        bb.encode_text(txt)
+    torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
+ms = timeit(both)
+print('image + text on two streams B=%d: %.3f ms' % (B, ms))
+def seq():
+    bb.encode_image(img); bb.encode_text(txt)
+ms = timeit(seq)
+print('image then text on one stream B=%d: %.3f ms' % (B, ms))
