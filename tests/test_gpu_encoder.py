@@ -135,6 +135,28 @@ def test_towers_match_oracle_on_fresh_batches(batch):
     assert torch.equal(bb.encode_image(image), bb.encode_image(image))
 
 
+def test_full_batch_properties_vit_b32():
+    """BASELINE size (batch 256, ViT-B/32), size-independent properties instead of a CPU oracle run:
+    batch invariance (a sample's features do not depend on what else is in the batch or where it sits: every output
+    element has a fixed K-order accumulation), permutation equivariance, and run-to-run determinism — all bit-exact."""
+    sd = synth.clip_state_dict(synth.VIT_B32, seed=11)
+    bb = encoder.ClipBackbone(sd)
+    image = synth.random_images(256, seed=123).cuda()
+    text, pad = synth.random_captions(256, seed=124)
+    text = text.cuda()
+    fi, ft = bb.encode_image(image), bb.encode_text(text)
+    assert torch.isfinite(fi).all() and torch.isfinite(ft).all()
+    assert torch.equal(fi, bb.encode_image(image)) and torch.equal(ft, bb.encode_text(text))
+    assert torch.equal(bb.encode_image(image[:7]), fi[:7]) and torch.equal(bb.encode_text(text[:7]), ft[:7])
+    assert torch.equal(bb.encode_image(image[100:133]), fi[100:133])
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(5)).cuda()
+    assert torch.equal(bb.encode_image(image[perm]), fi[perm]) and torch.equal(bb.encode_text(text[perm]), ft[perm])
+    # and the first rows against the fp32 oracle (the CPU finishes 4 samples in seconds)
+    with torch.no_grad():
+        check_features(fi[:4], port.encode_image(sd, image[:4].cpu()))
+        check_features(ft[:4], port.encode_text(sd, text[:4].cpu()))
+
+
 def test_residual_stream_error_stays_bounded_per_block():
     """Per-block check of the ViT-B/32 image tower against the oracle trace: the bf16 error must not compound."""
     sd = synth.clip_state_dict(synth.VIT_B32, seed=11)
