@@ -246,10 +246,9 @@ int attention_bf16(const void* qkv, int64_t B, int L, int H, const uint8_t* pad,
     } else if (L <= 64) {
         CMH_CUDA_TRY(launch_kernel(attn_kernel<64>, dim3(grid), dim3(128), 64 * 385, st, 1, p));
     } else {
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce once;
+        if (once.needs()) {
             CMH_CUDA_TRY(cudaFuncSetAttribute(attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 385));
-            configured = true;
         }
         CMH_CUDA_TRY(launch_kernel(attn_kernel<128>, dim3(grid), dim3(256), 128 * 385, st, 1, p));
     }

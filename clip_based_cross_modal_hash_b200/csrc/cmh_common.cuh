@@ -33,6 +33,18 @@ int sm_count_cached();                     // SM count of the current device (ca
         if (!(cond)) return ::cmh::fail(CMH_ERR_INVALID, __VA_ARGS__);                            \
     } while (0)
 
+// cudaFuncSetAttribute is a per-device setting: remember per device whether a kernel has been configured
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool needs() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -541,10 +541,9 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
 template <int BN, int CG>
 int launch_gemm(const CUtensorMap& ta, const void* W, int64_t ldw, GemmParams p, cudaStream_t st) {
     using C = GemmCfg<BN, CG>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.needs()) {
         CMH_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
     }
     p.tiles_m = int(ceil_div(p.M, BM * CG));
     p.tiles_n = int(ceil_div(p.N, BN));
