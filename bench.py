@@ -239,6 +239,8 @@ def bench_encode(args, dev, world, rank, barrier, all_max):
                      "unit": "TFLOP/s", "frac": ach / sustained, "frac_of_burst_peak": ach / burst, "peak_kind": kind + " cuBLAS bf16, sustained",
                      "traffic": None, "algorithmic_flops_per_image": fl, "tower_ms": tower_ms},
         "gpu_launches_per_step": 12 * 7 + 7,
+        "l2": "3 image batches of 154 MB are cycled (462 MB > 126 MB L2): every step reads its images from HBM",
+        "gpu_launches": (12 * 7 + 7) * steps * 2 + (12 * 7 + 6) * steps,
     }
     return out
 
@@ -414,6 +416,7 @@ def run_ours(args, cfg, name):
     }
     if encode is not None:
         line["encode"] = encode
+        line["gpu_launches"] += encode["gpu_launches"]
     if world == 1:
         names = (["pack", "hist_kernel", "scan", "rank_map_kernel", "map_finish"] if args.op == "map"
                  else ["pack", "hist_kernel", "scan", "rank_topk_kernel", "none"])
