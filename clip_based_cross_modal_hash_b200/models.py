@@ -137,7 +137,53 @@ class DcmhtHashLayer(_HeadBase):
         return self.encode_img(img_embeds), self.encode_txt(txt_embeds)
 
 
-class _Model(torch.nn.Module):
+def load_clip_state_dict(clip_path: str) -> Dict[str, torch.Tensor]:
+    """The checkpoint read of ``BaseModel.load_backbone`` (models/base.py:18-31): a TorchScript archive (the OpenAI
+    ``ViT-B-32.pt``) or a plain ``torch.save``d state dict."""
+    try:
+        return torch.jit.load(clip_path, map_location="cpu").eval().state_dict()
+    except RuntimeError:
+        return torch.load(clip_path, map_location="cpu")
+
+
+class _RegistryMixin:
+    """What ``BaseTrainer.build_model`` needs from a registered model (runners/base.py:98-107): ``from_config`` and a
+    ``state_dict`` / ``load_state_dict`` pair with the reference's key prefixes (``backbone.*``, ``hash.*``; other keys of a
+    trained checkpoint — loss parameters, feature buffers — are ignored: this path only evaluates)."""
+
+    HEAD_INIT = None   # synth generator used until a trained checkpoint is loaded
+
+    @classmethod
+    def from_config(cls, cfg, output_dim=16, train_num=10000, device="cuda"):
+        from . import synth
+
+        clip = load_clip_state_dict(cfg.get("clip_path", "./ViT-B-32.pt"))
+        embed_dim = clip["text_projection"].shape[1]
+        return cls(clip, getattr(synth, cls.HEAD_INIT)(embed_dim, output_dim, seed=0), device=device)
+
+    def state_dict(self, *a, **k):
+        out = {"backbone." + n: v for n, v in self.backbone.state_dict().items()}
+        out.update({"hash." + n: v for n, v in self.hash.state_dict().items()})
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        bb = {k[len("backbone."):]: v for k, v in state_dict.items() if k.startswith("backbone.")}
+        hh = {k[len("hash."):]: v for k, v in state_dict.items() if k.startswith("hash.")}
+        if strict and (not bb or not hh):
+            raise KeyError("expected keys with the prefixes 'backbone.' and 'hash.'")
+        if bb:
+            self.backbone.load_state_dict(bb, strict=strict)
+        if hh:
+            self.hash.load_state_dict(hh, strict=strict)
+
+    def float(self):           # runners/base.py:106-107 call .float() / .to(device): nothing to convert here
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+
+class _Model(_RegistryMixin, torch.nn.Module):
     HASH = None
 
     def __init__(self, clip_state_dict, hash_state_dict, device="cuda"):
@@ -168,6 +214,7 @@ class _Model(torch.nn.Module):
 
 class DSPH(_Model):
     HASH = DsphHashLayer
+    HEAD_INIT = "dsph_head_state_dict"
 
     @staticmethod
     def make_hash_code(code):               # runners/base.py:407-410 (in place, like the reference)
@@ -176,6 +223,7 @@ class DSPH(_Model):
 
 class DCMHT(_Model):
     HASH = DcmhtHashLayer
+    HEAD_INIT = "dcmht_head_state_dict"
 
     @staticmethod
     def make_hash_code(code):               # runners/DCMHT/runner.py:83-95
@@ -294,8 +342,10 @@ class MithHashLayer(_HeadBase):
         return self.encode_img(img_cls, img_tokens) + self.encode_txt(txt_eos, txt_tokens, key_padding_mask)
 
 
-class MITH(torch.nn.Module):
+class MITH(_RegistryMixin, torch.nn.Module):
     """models/MITH/MITH.py (evaluation mode): backbone with ``return_patches=True`` + ``MithHashLayer``."""
+
+    HEAD_INIT = "mith_head_state_dict"
 
     def __init__(self, clip_state_dict, hash_state_dict, device="cuda", top_k_label: int = 8):
         super().__init__()

@@ -266,6 +266,23 @@ def test_encode_to_map_pipeline_matches_float_path():
     assert float(got) == float(want)
 
 
+def test_registry_surface_from_config_and_checkpoint_roundtrip(tmp_path):
+    """BaseTrainer.build_model's calls (runners/base.py:98-107): from_config(cfg, output_dim, train_num) reads the CLIP
+    checkpoint from cfg['clip_path']; load_state_dict takes a trained checkpoint with backbone.* / hash.* keys."""
+    sd = synth.clip_state_dict(synth.TINY, seed=21)
+    ckpt = tmp_path / "clip_tiny.pt"
+    torch.save(sd, ckpt)                                  # load_backbone falls back to torch.load (models/base.py:23-24)
+    model = models.DSPH.from_config({"clip_path": str(ckpt)}, output_dim=32, train_num=100).float().to("cuda")
+    assert model.output_dim == 32 and hasattr(model, "backbone") and hasattr(model, "hash")
+    trained = models.DSPH(sd, synth.dsph_head_state_dict(synth.TINY["embed_dim"], 32, seed=99))
+    full = trained.state_dict()
+    assert any(k.startswith("backbone.visual.") for k in full) and "hash.img_hash.fc.weight" in full
+    full["hyp.proxies"] = torch.zeros(3, 32)              # loss parameters of a real checkpoint are ignored
+    model.load_state_dict(full)
+    image = synth.random_images(3, seed=1)
+    assert torch.equal(model.encode_image(image), trained.encode_image(image))
+
+
 def test_encoder_rejects_bad_arguments():
     sd = synth.clip_state_dict(synth.TINY, seed=1)
     bb = encoder.ClipBackbone(sd)
