@@ -115,6 +115,7 @@ PROTOTYPES = {
     "cmh_linear_f32": [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp],
     "cmh_head_dsph": [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "cmh_head_dcmht": [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp],
+    "cmh_hyp_loss_f32": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, ctypes.c_float, ctypes.c_float, _vp, _sz, _vp, _vp],
     "cmh_head_mith_workspace_bytes": [_vp, _i64, _i32],
     "cmh_head_mith": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp],
 }

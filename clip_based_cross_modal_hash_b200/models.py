@@ -212,6 +212,28 @@ class _Model(_RegistryMixin, torch.nn.Module):
         return self.hash._run(self.backbone.encode_text(text), "txt", True)[1]
 
 
+def hyp_loss(x, y, label, proxies, threshold: float, alpha: float = 0.8) -> torch.Tensor:
+    """Forward value of ``HyP.forward(x, y, label)`` (models/DSPH/loss/HyP.py:18-69) on the GPU -> 0-dim fp32 device tensor.
+    Evaluation / monitoring only: no gradient flows (the training step is out of this round's scope)."""
+    from . import retrieval as R
+
+    dev = x.device
+    if dev.type != "cuda":
+        raise _lib.CmhError("hyp_loss needs CUDA tensors (there is no CPU path)")
+    x, y = x.detach().float().contiguous(), y.detach().to(dev).float().contiguous()
+    proxies = proxies.detach().to(dev).float().contiguous()
+    B, K = x.shape
+    C = proxies.shape[0]
+    lab = R.pack_labels(label.detach().to(dev))
+    need = 256 + (2 * B + C) * K * 4
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cmh_hyp_loss_f32(x.data_ptr(), y.data_ptr(), lab.data_ptr(), proxies.data_ptr(), B, K, C,
+                                              float(threshold), float(alpha), ws.data_ptr(), ws.numel(), out.data_ptr(), _stream()))
+    return out
+
+
 class DSPH(_Model):
     HASH = DsphHashLayer
     HEAD_INIT = "dsph_head_state_dict"

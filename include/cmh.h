@@ -296,6 +296,15 @@ typedef struct cmh_dcmht_head {
 int cmh_head_dcmht(const float* feat, int64_t rows, int in_dim, const cmh_dcmht_head* head, int nbits, float* scratch,
                    float* probs, uint32_t* packed, void* stream);
 
+/* ---- L: objective value ---------------------------------------------------------------------------------------------
+ * cmh_hyp_loss_f32 == HyP.forward(x, y, label) (models/DSPH/loss/HyP.py:18-69), forward value only (evaluation /
+ * monitoring; no gradient).  x, y [B][nbits] fp32 (image / text hash outputs), labels_packed [B][LW] from
+ * cmh_pack_labels, proxies [ncls][nbits] fp32 (HyP.proxies), threshold / alpha as in the reference constructor.
+ * workspace >= 256 + (2B + ncls) * nbits * 4 bytes, 256-byte aligned.  loss_out: one fp32 on the device. */
+int cmh_hyp_loss_f32(const float* x, const float* y, const uint32_t* labels_packed, const float* proxies, int64_t batch,
+                     int nbits, int ncls, float threshold, float alpha, void* workspace, size_t workspace_bytes,
+                     float* loss_out, void* stream);
+
 /* MITH head, eval mode (models/MITH/hash/hash.py:193-254), one modality (HashLayer.encode_img / encode_txt).
  * Matrices of the residual MLPs, of the concept transformer and the concept projection are bf16 ([out][in]); the concept
  * embedding, the per-bit hashing weights and every vector are fp32. */
