@@ -13,7 +13,8 @@ gallery and the mAP scalar is produced.  metric = query x gallery pairs per seco
   e2e     the same through the reference-facing call calc_utils.calc_map_k(host tensors): pinned host buffers,
           H2D copies and the D2H of the result inside the timed region
   N > 1   weak scaling: every rank holds one gallery shard of the workload's size (total gallery = N x shard),
-          queries replicated; exchange = all-gather of per-shard histograms + AP partials (NCCL).
+          queries replicated; exchange (NCCL) = all-gather of per-shard bucket totals + AP partials (mAP) or bucket totals +
+          one all-reduce(MAX) of the [Q, k] key buffer (top-k; --topk-exchange allgather_merge = BASELINE's literal all-gather).
 
 --impl reference times the reference's own CPU evaluator (oracle/calc_utils_port.py: the same ATen CPU ops as
 common/calc_utils.py, the Python reference itself cannot travel to the GPU box) on a bounded query sample.
@@ -296,7 +297,7 @@ def run_ours(args, cfg, name):
         if args.op == "topk":
             mark()
             if world > 1:
-                keys = ev.topk(qp, gp, K, k, rank * N, n_geom=N)
+                keys = ev.topk(qp, gp, K, k, rank * N, n_geom=N, method=args.topk_exchange)
                 mark()
                 return keys
             pl = st.make_plan(Q, N, K, 0)
@@ -328,7 +329,7 @@ def run_ours(args, cfg, name):
         if args.op == "topk":
             qp = R.pack_codes(host[0].to(dev, non_blocking=True))
             gp = R.pack_codes(host[1].to(dev, non_blocking=True))
-            keys = ev.topk(qp, gp, K, k, rank * N, n_geom=N) if world > 1 else R.topk(qp, gp, K, k)
+            keys = ev.topk(qp, gp, K, k, rank * N, n_geom=N, method=args.topk_exchange) if world > 1 else R.topk(qp, gp, K, k)
             return pinned_keys.copy_(keys)
         if world == 1:
             return calc_utils.calc_map_k(host[0], host[1], host[2], host[3], k)
@@ -408,7 +409,8 @@ def run_ours(args, cfg, name):
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": name, "Q": Q, "N_per_gpu": N, "N_total": N * world, "bits": K, "classes": C, "k": k,
                    "step": "pack(+-1 fp32 codes, int64 labels) -> hist -> scan -> rank/AP -> mAP",
-                   "l2": "256 MiB flush write between timed steps", "op": args.op, "map": float(out.item()) if (out is not None and args.op == "map") else None},
+                   "l2": "256 MiB flush write between timed steps", "op": args.op,
+                   "topk_exchange": args.topk_exchange if (args.op == "topk" and world > 1) else None, "map": float(out.item()) if (out is not None and args.op == "map") else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16 if args.op == "map" else Q * k * 8,
                 "ms_per_step": e2e_total_ms / len(e2e_ms)},
         "gpu_launches": args.steps * 10,
@@ -461,6 +463,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--topk-exchange", default="rank_scatter", choices=["rank_scatter", "allgather_merge"])
     ap.add_argument("--no-encode", action="store_true", help="skip the CLIP encode section of the line")
     ap.add_argument("--op", default=None, choices=["map", "topk"],
                     help="map = calc_map_k (default for C1-C3); topk = Hamming + per-query top-k (default for C4-*)")

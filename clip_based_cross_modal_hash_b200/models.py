@@ -416,14 +416,15 @@ class MITH(_RegistryMixin, torch.nn.Module):
 
 def merge_code_buffers(*buffers, group=None):
     """Combine per-rank packed code buffers under the reference's DDP evaluation pattern (runners/base.py:259-264): every rank
-    filled only the rows of its own sampler indices, the rest is zero.  One bitwise-OR all-reduce of the PACKED buffers
-    (COCO 64-bit gallery: 0.94 MB) replaces the reference's barrier + fp32 all-reduce(SUM) of [length, K] floats (30 MB) — and
-    rows that DistributedSampler duplicated to pad the last batch stay correct (the reference sums them to +-2)."""
+    filled only the rows of its own sampler indices, the rest is zero.  One all-reduce of the PACKED buffers (COCO 64-bit
+    gallery: 0.94 MB) replaces the reference's barrier + fp32 all-reduce(SUM) of [length, K] floats (30 MB).  The reduction is
+    a byte-wise MAX (NCCL has no bitwise OR; against zero bytes MAX == OR), so rows that DistributedSampler duplicated to pad
+    the last batch stay correct — the reference sums them to +-2."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         for b in buffers:
-            dist.all_reduce(b, op=dist.ReduceOp.BOR, group=group)
+            dist.all_reduce(b.view(torch.uint8), op=dist.ReduceOp.MAX, group=group)
     return buffers
 
 

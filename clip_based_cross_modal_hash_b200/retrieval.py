@@ -344,7 +344,8 @@ class ShardedEvaluator:
 
     Exchange steps (all ``all_gather_into_tensor``; NCCL over NVLink on GPUs, gloo in the CPU tests):
       mAP    : per-shard bucket totals [2, bins, Qpad] int32  ->  scan  ->  per-chunk AP partials fp64
-      top-k  : per-shard partial top-k keys [Q, k] int64 (ONE all-gather) -> merge kernel
+      top-k  : per-shard bucket totals -> every item's global rank -> ONE all-reduce(MAX) of the [Q, k] key buffer
+               (or, method="allgather_merge": per-shard partial top-k keys, ONE all-gather, merge kernel)
     Every rank ends with the identical result.
     """
 
@@ -390,14 +391,31 @@ class ShardedEvaluator:
             self.dist.all_reduce(tindex, op=self.dist.ReduceOp.SUM, group=self.group)
         return MapResult(m, ap, sc["tsum"][:Q], sc["total"][:Q], tindex)
 
-    def topk(self, qp, gp_local, nbits: int, k: int, idx_offset: int, n_geom: Optional[int] = None) -> torch.Tensor:
-        """north_star exchange: per-shard partial top-k, ONE all-gather, merge."""
+    def topk(self, qp, gp_local, nbits: int, k: int, idx_offset: int, n_geom: Optional[int] = None,
+             method: str = "rank_scatter") -> torch.Tensor:
+        """Global top-k keys [Q, k] (identical on every rank) of a gallery sharded by contiguous index range.
+
+        ``rank_scatter`` (default): the counting formulation gives every item its GLOBAL stable rank from this rank's own
+        histogram plus the other ranks' per-bucket totals (one 2*bins*Qpad*4-byte all-gather, 2.6 MB at 10k queries x 64 bit),
+        so each rank writes its items straight into their final slots of a [Q, k] buffer (untouched slots stay EMPTY = -1) and
+        ONE all-reduce(MAX) of that buffer (80 MB at C4) finishes the job — no partial lists, no merge kernel.
+        ``allgather_merge``: BASELINE.json's literal exchange — per-shard partial top-k, one all-gather of [Q, k] keys per rank
+        (8 x 80 MB at C4), merge kernel.  Both are exact and give the same keys (tests/test_sharded_gloo.py, check_multi_gpu.py).
+        """
         st = self.stages
         Q, n_local = qp.shape[0], gp_local.shape[0]
         n_geom = self._geometry(n_local, n_geom, qp.device)
         plan = st.make_plan(Q, n_local, nbits, 0, n_geom)
         hist = st.hist(plan, qp, None, gp_local, None)
-        sc = st.scan(plan, hist, 1, 0, k, with_rel=False)      # local ranking of this shard
-        keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset)
-        parts = self._gather(keys)                             # [world, Q, k]
-        return st.topk_merge(parts)
+        if method == "allgather_merge":
+            sc = st.scan(plan, hist, 1, 0, k, with_rel=False)      # local ranking of this shard
+            keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset)
+            parts = self._gather(keys)                             # [world, Q, k]
+            return st.topk_merge(parts)
+        if method != "rank_scatter":
+            raise CmhError("unknown top-k exchange %r" % method)
+        totals_all = self._gather(st.hist_totals(plan, hist))      # [world, 2, bins, Qpad]
+        sc = st.scan_sharded(plan, hist, totals_all, self.world, self.rank, k)
+        keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset)  # slots of global rank < k owned by this shard
+        self.dist.all_reduce(keys, op=self.dist.ReduceOp.MAX, group=self.group)   # EMPTY = -1 < every real key
+        return keys

@@ -38,8 +38,9 @@ def main():
         kk = k or 1000
         keys1 = R.topk(qp, gp, K, kk)
         keys = ev.topk(qp, gp[lo:hi], K, kk, lo)
+        keys_ag = ev.topk(qp, gp[lo:hi], K, kk, lo, method="allgather_merge")
         good = (torch.equal(res.tindex, single.tindex) and torch.equal(res.total, single.total)
-                and abs(res.map.item() - single.map.item()) < 1e-12 and torch.equal(keys, keys1))
+                and abs(res.map.item() - single.map.item()) < 1e-12 and torch.equal(keys, keys1) and torch.equal(keys_ag, keys1))
         if rank == 0:
             from oracle import c_oracle, hamming_oracle as ho
             W = (K + 31) // 32

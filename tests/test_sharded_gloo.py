@@ -46,7 +46,9 @@ def _worker(rank, world, port, name, out_dir):
         ev = R.ShardedEvaluator(stages=OracleStages())
         cap = max(int(c.totals.max()), 1)
         res = ev.map_k(qp, qlp, gp[lo:hi], glp[lo:hi], c.K, c.C, c.k, tindex_cap=cap)
-        keys = ev.topk(qp, gp[lo:hi], c.K, 50, lo)
+        keys = ev.topk(qp, gp[lo:hi], c.K, 50, lo)                                   # rank_scatter: one all-reduce(MAX)
+        keys_ag = ev.topk(qp, gp[lo:hi], c.K, 50, lo, method="allgather_merge")      # BASELINE's all-gather + merge
+        assert torch.equal(keys, keys_ag)
         torch.save({"map": res.map, "total": res.total, "tsum": res.tsum, "tindex": res.tindex, "keys": keys},
                    os.path.join(out_dir, "r%d.pt" % rank))
     finally:
@@ -92,7 +94,7 @@ def _merge_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_merge_code_buffers_bitwise_or_survives_sampler_padding():
+def test_merge_code_buffers_survives_sampler_padding():
     """get_code's distributed merge: packed buffers, bitwise OR, duplicated (padded) rows stay exact."""
     import torch.multiprocessing as mp
 
