@@ -50,6 +50,20 @@ def main():
             good = good and np.array_equal(res.tindex.cpu().numpy()[sub], tix)
             print("Q=%d N=%d K=%d k=%s world=%d: %s  mAP=%.9f" % (Q, N, K, k, world, "OK" if good else "MISMATCH", res.map.item()), flush=True)
         ok = ok and good
+    # get_code's distributed merge of packed code buffers (byte-wise MAX over NCCL), with DistributedSampler-style padding
+    from clip_based_cross_modal_hash_b200 import models
+    g = torch.Generator().manual_seed(0)
+    n = 8 * world + 3
+    full = torch.randint(-2 ** 31, 2 ** 31 - 1, (n, 2), generator=g, dtype=torch.int64).to(torch.int32).to(dev)
+    padded = list(range(n)) + list(range((-n) % world))
+    mine = torch.tensor(padded[rank::world], device=dev)
+    buf = torch.zeros_like(full)
+    buf[mine] = full[mine]
+    models.merge_code_buffers(buf)
+    good = bool(torch.equal(buf, full))
+    if rank == 0:
+        print("merge_code_buffers world=%d: %s" % (world, "OK" if good else "MISMATCH"), flush=True)
+    ok = ok and good
     t = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(t)
     dist.destroy_process_group()
