@@ -19,9 +19,6 @@ import torch
 
 from . import _lib
 
-_f32p, _vp = ctypes.c_void_p, ctypes.c_void_p
-
-
 class BlockWeights(ctypes.Structure):
     """Mirror of ``struct cmh_block_weights``."""
 
