@@ -80,16 +80,25 @@ __global__ void __launch_bounds__(LP * 2, LP == 128 ? 2 : (LP == 64 ? 7 : 12)) a
     const __nv_bfloat16* base = p.qkv + size_t(b) * L * 3 * D + h * DH;
 
     pdl_wait();
-    // Q and K first (one cp.async group), V second: S = Q.K^T and the softmax run while V is still in flight
+    // Q and K first (one cp.async group), V second: S = Q.K^T and the softmax run while V is still in flight.
+    // A thread copies the same 16-byte column chunk of 4 rows (LP/4 apart) of each part: one swizzled shared offset and one
+    // global pointer per thread, constants added per copy (the generic index arithmetic was half of the kernel's instructions).
+    {
+        constexpr int RPP = LP / 4;  // rows per pass = threads / 8
+        const int r0 = tid >> 3, c = tid & 7;
+        const uint32_t soff = uint32_t(r0 * 128 + ((c ^ (r0 & 7)) << 4));  // (r0 + j*RPP) & 7 == r0 & 7
+        const __nv_bfloat16* g0 = base + size_t(r0) * 3 * D + c * 8;
+        const size_t gstep = size_t(RPP) * 3 * D;
 #pragma unroll
-    for (int part = 0; part < 3; ++part) {
-        uint8_t* dstp = part == 0 ? sq : part == 1 ? sk : sv;
-        for (int i = tid; i < LP * 8; i += LP * 2) {
-            const int r = i >> 3, c = i & 7;
-            const bool valid = r < L;
-            cp_async16(dstp + tile_off(r, c), base + size_t(valid ? r : 0) * 3 * D + part * D + c * 8, valid);
+        for (int part = 0; part < 3; ++part) {
+            uint8_t* dstp = (part == 0 ? sq : part == 1 ? sk : sv) + soff;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool valid = r0 + j * RPP < L;
+                cp_async16(dstp + j * RPP * 128, valid ? g0 + part * D + j * gstep : base, valid);
+            }
+            if (part >= 1) cp_async_commit();
         }
-        if (part >= 1) cp_async_commit();
     }
     for (int j = tid; j < LP; j += LP * 2) spad[j] = (j >= L) || (p.pad && p.pad[size_t(b) * L + j]);
     cp_async_wait_group<1>();
@@ -105,14 +114,18 @@ __global__ void __launch_bounds__(LP * 2, LP == 128 ? 2 : (LP == 64 ? 7 : 12)) a
     if (active) {
 #pragma unroll
     for (int n = 0; n < NT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    // ldmatrix lane addresses: row term once, the swizzled 16-byte chunk per k-step from (chunk ^ (row & 7)), row & 7 == lane & 7
+    const uint32_t q_row = q_base + uint32_t((warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * 128);
+    const uint32_t k_row = k_base + uint32_t(((lane >> 4) * 8 + (lane & 7)) * 128);
 #pragma unroll
     for (int ks = 0; ks < DH / 16; ++ks) {
         uint32_t a0, a1, a2, a3;
-        ldsm_x4(q_base + tile_off(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)), a0, a1, a2, a3);
+        ldsm_x4(q_row + uint32_t(((ks * 2 + (lane >> 4)) ^ (lane & 7)) << 4), a0, a1, a2, a3);
+        const uint32_t k_sw = uint32_t(((ks * 2 + ((lane >> 3) & 1)) ^ (lane & 7)) << 4);
 #pragma unroll
         for (int n = 0; n < NT; n += 2) {
             uint32_t b0, b1, b2, b3;
-            ldsm_x4(k_base + tile_off(n * 8 + (lane >> 4) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+            ldsm_x4(k_row + n * 1024 + k_sw, b0, b1, b2, b3);
             mma_bf16(s[n], a0, a1, a2, a3, b0, b1);
             mma_bf16(s[n + 1], a0, a1, a2, a3, b2, b3);
         }
@@ -125,17 +138,20 @@ __global__ void __launch_bounds__(LP * 2, LP == 128 ? 2 : (LP == 64 ? 7 : 12)) a
 #pragma unroll
     for (int w = 0; w < LP / 32; ++w) dead[w] = __ballot_sync(0xffffffffu, spad[w * 32 + lane] != 0);
     float m0 = -INFINITY, m1 = -INFINITY;
+    const bool any_mask = p.causal || p.pad != nullptr;  // image tower: only the tail tiles (columns >= L) need masking
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
+        if (any_mask || n * 8 + 8 > L) {  // warp-uniform
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int j = n * 8 + (lane & 3) * 2 + e;
-            const bool gone = (dead[(n * 8) / 32] >> (j & 31)) & 1u;
-            if (gone || (p.causal && j > r0)) s[n][e] = -INFINITY;
-            if (gone || (p.causal && j > r1)) s[n][2 + e] = -INFINITY;
-            m0 = fmaxf(m0, s[n][e]);
-            m1 = fmaxf(m1, s[n][2 + e]);
+            for (int e = 0; e < 2; ++e) {
+                const int j = n * 8 + (lane & 3) * 2 + e;
+                const bool gone = (dead[(n * 8) / 32] >> (j & 31)) & 1u;
+                if (gone || (p.causal && j > r0)) s[n][e] = -INFINITY;
+                if (gone || (p.causal && j > r1)) s[n][2 + e] = -INFINITY;
+            }
         }
+        m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
+        m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
     }
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
@@ -184,6 +200,7 @@ __global__ void __launch_bounds__(LP * 2, LP == 128 ? 2 : (LP == 64 ? 7 : 12)) a
     float o[DH / 8][4];
 #pragma unroll
     for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    const uint32_t v_row = v_base + uint32_t((((lane >> 3) & 1) * 8 + (lane & 7)) * 128);  // + kk*16 rows per step
 #pragma unroll
     for (int kk = 0; kk < LP / 16; ++kk) {
         const uint32_t a0 = pack2(s[2 * kk][0], s[2 * kk][1]), a1 = pack2(s[2 * kk][2], s[2 * kk][3]);
@@ -191,7 +208,7 @@ __global__ void __launch_bounds__(LP * 2, LP == 128 ? 2 : (LP == 64 ? 7 : 12)) a
 #pragma unroll
         for (int dn = 0; dn < DH / 8; dn += 2) {
             uint32_t b0, b1, b2, b3;
-            ldsm_x4_t(v_base + tile_off(kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), dn + (lane >> 4)), b0, b1, b2, b3);
+            ldsm_x4_t(v_row + kk * 2048 + uint32_t(((dn + (lane >> 4)) ^ (lane & 7)) << 4), b0, b1, b2, b3);
             mma_bf16(o[dn], a0, a1, a2, a3, b0, b1);
             mma_bf16(o[dn + 1], a0, a1, a2, a3, b2, b3);
         }
@@ -199,18 +216,30 @@ __global__ void __launch_bounds__(LP * 2, LP == 128 ? 2 : (LP == 64 ? 7 : 12)) a
 
     // ---- normalise, stage through this warp's own (now dead) Q rows, store 16 bytes per lane --------------
     __syncwarp();
+    {
+        const uint32_t st0 = q_base + uint32_t(r0 * 128 + (lane & 3) * 4), st1 = st0 + 8 * 128;  // r1 = r0 + 8, same row & 7
+        const int sw = r0 & 7;
 #pragma unroll
-    for (int n = 0; n < DH / 8; ++n) {
-        *reinterpret_cast<uint32_t*>(sq + tile_off(r0, n) + (lane & 3) * 4) = pack2(o[n][0] * inv0, o[n][1] * inv0);
-        *reinterpret_cast<uint32_t*>(sq + tile_off(r1, n) + (lane & 3) * 4) = pack2(o[n][2] * inv1, o[n][3] * inv1);
+        for (int n = 0; n < DH / 8; ++n) {
+            const uint32_t off = uint32_t((n ^ sw) << 4);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(st0 + off), "r"(pack2(o[n][0] * inv0, o[n][1] * inv0)) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(st1 + off), "r"(pack2(o[n][2] * inv1, o[n][3] * inv1)) : "memory");
+        }
     }
     __syncwarp();
+    {
+        const int c = lane & 7, rr = lane >> 3;  // 8 lanes cover one 128-byte row; 4 rows per instruction
+        __nv_bfloat16* orow = p.out + (size_t(b) * L + warp * 16 + rr) * D + h * DH + c * 8;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int idx = lane + 32 * i, r = warp * 16 + (idx >> 3), c = idx & 7;
-        if (r < L) {
-            const uint4 v = *reinterpret_cast<const uint4*>(sq + tile_off(r, c));
-            *reinterpret_cast<uint4*>(p.out + (size_t(b) * L + r) * D + h * DH + c * 8) = v;
+        for (int i = 0; i < 4; ++i) {
+            const int r = warp * 16 + rr + 4 * i;
+            if (r < L) {
+                uint4 v;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                             : "r"(q_base + uint32_t(r * 128 + ((c ^ (r & 7)) << 4))));
+                *reinterpret_cast<uint4*>(orow + size_t(4 * i) * D) = v;
+            }
         }
     }
 }
