@@ -107,6 +107,7 @@ PROTOTYPES = {
     "cmh_gemm_set_trace": [_vp],
     "cmh_gemm_force_units": [_i32],
     "cmh_gemm_tail_slicing": [_i32],
+    "cmh_gemm_mma_lookahead": [_i32],
     "cmh_encoder_workspace_bytes": [_vp, _i64, _i32],
     "cmh_encode_image": [_vp, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp],
     "cmh_encode_text": [_vp, _vp, _vp, _i64, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp],

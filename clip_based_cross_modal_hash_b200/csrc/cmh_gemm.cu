@@ -67,6 +67,7 @@ struct GemmParams {
     // work items: [0, tail_start) are full (CG*128) x BN tiles; the tiles of the last, partial wave are cut into
     // 2^tail_shift column slices each (one item per slice) so that the wave ends after a slice, not after a tile
     int tail_start, tail_shift, num_items;
+    int lookahead;  // k-blocks the MMA warp may have queued in the tensor pipe
     long long* trace;  // debug timeline (cmh_gemm_set_trace): [cta][64] SM clock stamps, or null
 };
 
@@ -362,8 +363,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     // Keep at most MMA_LOOKAHEAD k-blocks queued in the tensor pipe.  tcgen05.ld of the epilogue warps is
                     // served in order behind the queued MMAs: with the whole 6-stage ring issued ahead, every TMEM load
                     // waited ~3000 clk and the epilogue fell behind the main loop (profiles/README.md).
-                    if (issued >= MMA_LOOKAHEAD) {
-                        const int g = issued - MMA_LOOKAHEAD;
+                    if (issued >= p.lookahead) {
+                        const int g = issued - p.lookahead;
                         mbar_wait(&empty[g % C::STAGES], uint32_t(g / C::STAGES) & 1u);
                     }
                     mbar_wait(&full[stage], phase);
@@ -501,7 +502,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 long long* g_trace = nullptr;
-int g_force_bn = 0, g_force_cg = 0, g_force_units = 0;
+int g_force_bn = 0, g_force_cg = 0, g_force_units = 0, g_lookahead = MMA_LOOKAHEAD;
 bool g_tail_slicing = true;  // test/bench hook (cmh_gemm_force_tile): 0 = automatic
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -614,6 +615,7 @@ int gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, i
     GemmParams p{};
     p.M = M, p.N = N, p.K = K, p.bias = bias, p.out = out, p.ldo = ldo, p.resid = resid, p.ldr = ldr, p.epi = epi;
     p.trace = g_trace;
+    p.lookahead = g_lookahead;
     if (cg == 2) {
         switch (bn) {
             case 256: return launch_gemm<256, 2>(ta, W, ldw, p, st);
@@ -639,6 +641,12 @@ extern "C" int cmh_gemm_force_tile(int bn, int cta_group) {
     if (!(bn == 0 || bn == 128 || bn == 192 || bn == 256) || cta_group < 0 || cta_group > 2)
         return cmh::fail(CMH_ERR_INVALID, "gemm_force_tile: bn in {0,128,192,256}, cta_group in {0,1,2}");
     cmh::g_force_bn = bn, cmh::g_force_cg = cta_group;
+    return CMH_OK;
+}
+
+extern "C" int cmh_gemm_mma_lookahead(int kblocks) {  // debug / tuning: 1..8, default MMA_LOOKAHEAD
+    if (kblocks < 1 || kblocks > 8) return cmh::fail(CMH_ERR_INVALID, "gemm_mma_lookahead: 1..8");
+    cmh::g_lookahead = kblocks;
     return CMH_OK;
 }
 

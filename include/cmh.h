@@ -204,6 +204,7 @@ int cmh_gemm_force_tile(int bn, int cta_group);
  * (0 entry, 1 set-up done, 2+4i.. per tile: accumulator wait / free / first operands landed / all MMAs issued,
  * 34+2i.. epilogue start / end of tile i, 63 exit). */
 int cmh_gemm_set_trace(long long* device_buffer);
+int cmh_gemm_mma_lookahead(int kblocks); /* tuning: k-blocks (4 MMAs each) the issuer may queue ahead, 1..8 (default 2) */
 int cmh_gemm_tail_slicing(int on);   /* debug: 0 disables the column slicing of the last partial wave's tiles */
 int cmh_gemm_force_units(int units); /* debug: cap the persistent grid at `units` CTAs (pairs for cta_group 2); 0 = all SMs */
 
