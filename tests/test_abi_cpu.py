@@ -79,3 +79,50 @@ def test_product_fails_loudly_without_cuda():
         cu.calc_hammingDist(a, a)
     with pytest.raises(_lib.CmhError):
         R.pack_codes(a)
+
+
+def test_encoder_workspace_queries_run_on_the_host():
+    """cmh_encoder_workspace_bytes / cmh_head_mith_workspace_bytes are pure host arithmetic (no GPU needed)."""
+    from clip_based_cross_modal_hash_b200 import encoder, models
+
+    lib = _lib.lib()
+    blocks = (encoder.BlockWeights * 12)()
+    t = encoder.Tower()
+    t.width, t.layers, t.heads, t.out_dim, t.blocks, t.patch, t.resolution = 768, 12, 12, 512, blocks, 32, 224
+    one = lib.cmh_encoder_workspace_bytes(ctypes.byref(t), 1, 50)
+    big = lib.cmh_encoder_workspace_bytes(ctypes.byref(t), 256, 50)
+    # x fp32 + h + qkv + att + fc (bf16) per token row = 768 * (4 + 2 + 6 + 2 + 8) bytes
+    assert big >= 256 * 50 * 768 * 22 and big < 256 * 50 * 768 * 24 and 0 < one < big
+    assert lib.cmh_encoder_workspace_bytes(ctypes.byref(t), 0, 50) == 0
+    h = models.MithHeadStruct()
+    h.dim, h.nbits, h.mlp_layers, h.top_k = 512, 64, 2, 8
+    h.transformer.width, h.transformer.layers, h.transformer.heads, h.transformer.out_dim = 512, 2, 8, 512
+    h.transformer.blocks = (encoder.BlockWeights * 2)()
+    assert lib.cmh_head_mith_workspace_bytes(ctypes.byref(h), 256, 49) > 256 * 49 * 512 * 4
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_encoders_fail_loudly_without_cuda():
+    from clip_based_cross_modal_hash_b200 import encoder, models, synth
+
+    sd = synth.clip_state_dict(synth.TINY, seed=1)
+    with pytest.raises(_lib.CmhError):
+        encoder.ClipBackbone(sd, device="cpu")
+    with pytest.raises((_lib.CmhError, RuntimeError, AssertionError)):   # torch refuses the CUDA allocation first
+        models.DSPH(sd, synth.dsph_head_state_dict(synth.TINY["embed_dim"], 16))
+    with pytest.raises(_lib.CmhError):
+        models.hyp_loss(torch.zeros(4, 16), torch.zeros(4, 16), torch.ones(4, 3), torch.zeros(3, 16), 0.0)
+
+
+def test_synth_generators_are_deterministic_and_shaped_like_the_reference():
+    from clip_based_cross_modal_hash_b200 import synth
+
+    a, b = synth.clip_state_dict(synth.TINY, seed=3), synth.clip_state_dict(synth.TINY, seed=3)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    assert a["visual.conv1.weight"].shape == (128, 3, 32, 32) and a["visual.positional_embedding"].shape == (50, 128)
+    assert a["text_projection"].shape == (128, 128) and a["token_embedding.weight"].shape[0] == synth.TINY["vocab_size"]
+    text, pad = synth.random_captions(9, seed=2)
+    assert text.shape == (9, 32) and bool((text.argmax(dim=-1) >= 3).all()) and bool((text[:, 0] == 49406).all())
+    assert torch.equal(pad, text == 0) and bool((text.max(dim=-1).values == 49407).all())
+    m = synth.mith_head_state_dict(512, 16, seed=1)
+    assert all(torch.equal(m["gcl_i." + k[6:]], v) for k, v in m.items() if k.startswith("gcl_t."))
