@@ -103,7 +103,7 @@ int project(const cmh_tower* t, const Workspace& w, int64_t B, int L, const int3
 
 // ---- MITH head -------------------------------------------------------------------------------------------------
 struct MithWs {
-    float *xc, *xt, *concept, *projout;
+    float *xc, *xt, *concept, *projout, *h32, *g32;
     void *hc, *gc, *ht, *gt, *x2b;
     void* tw;  // transformer workspace (carve)
     int64_t tw_bytes, bytes;
@@ -122,8 +122,11 @@ MithWs carve_mith(const cmh_mith_head* h, int64_t B, int L, void* base) {
     w.hc = take(B * D * 2);
     w.gc = take(B * 4 * D * 2);
     w.xt = static_cast<float*>(take(M * D * 4));
-    w.ht = take(M * D * 2);
-    w.gt = take(M * 4 * D * 2);
+    const bool split = h->mlp_layers > 0 && h->w1_split[0] != nullptr;
+    w.ht = take(M * D * 2 * (split ? 3 : 1));          // split precision: [hi | hi | lo]
+    w.gt = take(M * 4 * D * 2 * (split ? 3 : 1));
+    w.h32 = static_cast<float*>(take(split ? M * D * 4 : 0));
+    w.g32 = static_cast<float*>(take(split ? M * 4 * D * 4 : 0));
     w.concept = static_cast<float*>(take(M * K * 4));
     w.x2b = take(M2 * D * 2);
     w.projout = static_cast<float*>(take(M2 * D * 4));
@@ -133,11 +136,24 @@ MithWs carve_mith(const cmh_mith_head* h, int64_t B, int L, void* base) {
     return w;
 }
 
-// ResidualMLPs.forward (hash.py:34-37) on `rows` rows of the fp32 stream x, in place
-int res_mlps(const cmh_mith_head* h, float* x, void* hb, void* gb, int64_t rows, cudaStream_t st) {
+// ResidualMLPs.forward (hash.py:34-37) on `rows` rows of the fp32 stream x, in place.  h32/g32 non-null: split precision
+// (fp32 LayerNorm and GELU outputs are split into bf16 hi/lo parts and multiplied with the split weights, K concatenated).
+int res_mlps(const cmh_mith_head* h, float* x, void* hb, void* gb, float* h32, float* g32, int64_t rows, cudaStream_t st) {
     const int64_t D = h->dim;
     for (int i = 0; i < h->mlp_layers; ++i) {
         CMH_REQUIRE(h->w1[i] && h->w2[i] && h->ln_gain[i] && h->ln_bias[i], "mith: residual MLP %d has null weights", i);
+        if (h32) {
+            CMH_REQUIRE(h->w1_split[i] && h->w2_split[i], "mith: residual MLP %d lacks the split weights", i);
+            if (int rc = layernorm(x, rows, int(D), 1, nullptr, h->ln_gain[i], h->ln_bias[i], LN_EPS, h32, true, st)) return rc;
+            if (int rc = split3_bf16(h32, hb, rows, int(D), st)) return rc;
+            if (int rc = gemm_bf16(hb, rows, 3 * D, 3 * D, h->w1_split[i], 4 * D, 3 * D, h->b1[i], CMH_EPI_ERF_GELU_F32, g32, 4 * D,
+                                   nullptr, 0, st))
+                return rc;
+            if (int rc = split3_bf16(g32, gb, rows, int(4 * D), st)) return rc;
+            if (int rc = gemm_bf16(gb, rows, 12 * D, 12 * D, h->w2_split[i], D, 12 * D, h->b2[i], CMH_EPI_RESID_F32, x, D, x, D, st))
+                return rc;
+            continue;
+        }
         if (int rc = layernorm(x, rows, int(D), 1, nullptr, h->ln_gain[i], h->ln_bias[i], LN_EPS, hb, false, st)) return rc;
         if (int rc = gemm_bf16(hb, rows, D, D, h->w1[i], 4 * D, D, h->b1[i], CMH_EPI_ERF_GELU_BF16, gb, 4 * D, nullptr, 0, st)) return rc;
         if (int rc = gemm_bf16(gb, rows, 4 * D, 4 * D, h->w2[i], D, 4 * D, h->b2[i], CMH_EPI_RESID_F32, x, D, x, D, st)) return rc;
@@ -173,14 +189,15 @@ int cmh_head_mith(const cmh_mith_head* h, const float* cls, const float* tokens,
     cudaStream_t st = as_stream(stream);
     // global branch: res_cls, cls_hash = gcl(cls)   (hash.py:233-234, 98-106)
     if (int rc = gather_rows(cls, w.xc, B, 1, 1, 0, int(D), st)) return rc;
-    if (int rc = res_mlps(h, w.xc, w.hc, w.gc, B, st)) return rc;
+    if (int rc = res_mlps(h, w.xc, w.hc, w.gc, nullptr, nullptr, B, st)) return rc;
     if (int rc = linear_f32(w.xc, B, int(D), h->w_concept, nullptr, int(K), nullptr, nullptr, CMH_ACT_TANH, cls_hash, K, st)) return rc;
     if (res_cls) {
         if (int rc = normalize_rows(w.xc, B, int(D), res_cls, st)) return rc;
     }
     // local branch: concept embedding of every token (hash.py:235), aggregation to K concept tokens (+ position)
     if (int rc = gather_rows(tokens, w.xt, B, L, per_sample, first, int(D), st)) return rc;
-    if (int rc = res_mlps(h, w.xt, w.ht, w.gt, B * L, st)) return rc;
+    const bool split = h->mlp_layers > 0 && h->w1_split[0] != nullptr;
+    if (int rc = res_mlps(h, w.xt, w.ht, w.gt, split ? w.h32 : nullptr, split ? w.g32 : nullptr, B * L, st)) return rc;
     if (int rc = linear_f32(w.xt, B * L, int(D), h->w_concept, nullptr, int(K), nullptr, nullptr, CMH_ACT_TANH, w.concept, K, st)) return rc;
     const Workspace tw = carve(&h->transformer, B, int(K), w.tw);
     if (int rc = token_aggregation(w.concept, tokens, pad, h->pos, B, L, int(K), int(D), per_sample, first, h->top_k, tw.x, st)) return rc;

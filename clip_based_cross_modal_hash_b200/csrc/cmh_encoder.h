@@ -38,5 +38,6 @@ int token_aggregation(const float* concept, const float* x, const uint8_t* pad, 
 int bit_hash(const float* x, const float* w, const float* bias, int64_t rows, int K, int D, float* out, cudaStream_t st);
 int normalize_rows(const float* x, int64_t rows, int D, float* out, cudaStream_t st);
 int cast_bf16(const float* x, void* out, int64_t n, cudaStream_t st);
+int split3_bf16(const float* x, void* out, int64_t M, int D, cudaStream_t st);
 int add_sign_pack(const float* a, const float* b, int64_t rows, int nbits, uint32_t* packed, cudaStream_t st);
 }  // namespace cmh

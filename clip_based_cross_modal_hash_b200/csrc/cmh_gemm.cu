@@ -456,6 +456,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (p.epi == CMH_EPI_TANH_F32) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+                    } else if (p.epi == CMH_EPI_ERF_GELU_F32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
                     }
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -598,7 +601,7 @@ int gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, i
     CMH_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "gemm: bad arguments");
     CMH_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "gemm: leading dimensions must be multiples of 8 elements");
     CMH_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemm: operands must be 16-byte aligned");
-    CMH_REQUIRE(epi >= CMH_EPI_BF16 && epi <= CMH_EPI_ERF_GELU_BF16, "gemm: unknown epilogue %d", epi);
+    CMH_REQUIRE(epi >= CMH_EPI_BF16 && epi <= CMH_EPI_ERF_GELU_F32, "gemm: unknown epilogue %d", epi);
     CMH_REQUIRE(N % ((epi == CMH_EPI_BF16 || epi == CMH_EPI_GELU_BF16 || epi == CMH_EPI_ERF_GELU_BF16) ? 8 : 4) == 0,
                 "gemm: N = %lld must be a multiple of the 16-byte output vector", (long long)N);
     CMH_REQUIRE(epi != CMH_EPI_RESID_F32 || resid, "gemm: residual epilogue needs resid");

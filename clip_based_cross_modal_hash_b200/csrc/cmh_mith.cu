@@ -149,6 +149,26 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict
     }
 }
 
+// fp32 rows [M][D] -> bf16 rows [M][3D] = [hi | hi | lo], hi = bf16(x), lo = bf16(x - hi): the A operand of a K-concatenated
+// split-precision GEMM against W' = [W_hi | W_lo | W_hi]
+__global__ void split3_kernel(const float4* __restrict__ x, uint2* __restrict__ out, int64_t M, int d4) {
+    const int64_t total = M * d4;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t m = i / d4;
+        const int c = int(i % d4);
+        const float4 v = x[i];
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+        const uint2 hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        const uint2 lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        uint2* row = out + m * (3 * d4);
+        row[c] = hi;
+        row[d4 + c] = hi;
+        row[2 * d4 + c] = lo;
+    }
+}
+
 // MITHTrainer.generate_hash + make_hash_code (runners/MITH/runner.py:125-131): bit = (cls_hash + tokens_hash) > 0
 __global__ void add_sign_pack_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t rows, int nbits, int W,
                                      uint32_t* __restrict__ packed) {
@@ -202,6 +222,12 @@ int normalize_rows(const float* x, int64_t rows, int D, float* out, cudaStream_t
 int cast_bf16(const float* x, void* out, int64_t n, cudaStream_t st) {
     cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(out), n / 4);
     CMH_LAUNCH_CHECK("cast_bf16_kernel");
+    return CMH_OK;
+}
+
+int split3_bf16(const float* x, void* out, int64_t M, int D, cudaStream_t st) {
+    split3_kernel<<<grid_for(M * (D / 4), 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(out), M, D / 4);
+    CMH_LAUNCH_CHECK("split3_kernel");
     return CMH_OK;
 }
 

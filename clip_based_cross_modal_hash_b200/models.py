@@ -259,7 +259,7 @@ class MithHeadStruct(ctypes.Structure):
     _P4 = ctypes.c_void_p * 4
     _fields_ = [("dim", ctypes.c_int32), ("nbits", ctypes.c_int32), ("mlp_layers", ctypes.c_int32), ("top_k", ctypes.c_int32),
                 ("ln_gain", _P4), ("ln_bias", _P4), ("w1", _P4), ("b1", _P4), ("w2", _P4), ("b2", _P4),
-                ("w_concept", ctypes.c_void_p), ("pos", ctypes.c_void_p), ("transformer", Tower),
+                ("w1_split", _P4), ("w2_split", _P4), ("w_concept", ctypes.c_void_p), ("pos", ctypes.c_void_p), ("transformer", Tower),
                 ("w_bits", ctypes.c_void_p), ("b_bits", ctypes.c_void_p), ("w_cproj", ctypes.c_void_p), ("b_cproj", ctypes.c_void_p)]
 
 
@@ -267,8 +267,10 @@ class MithHashLayer(_HeadBase):
     """models/MITH/hash/hash.py:193-254 ``HashLayer`` (evaluation mode): global concept learning on the CLS/EOS feature,
     localized token aggregation + a small transformer + bitwise hashing on the token features."""
 
-    def __init__(self, state_dict, device, top_k_label: int = 8):
+    def __init__(self, state_dict, device, top_k_label: int = 8, split_precision: bool = True):
         self.top_k = top_k_label
+        # the token path feeds a discontinuous top-k selection: its MLP GEMMs run on hi/lo-split bf16 operands by default
+        self.split_precision = split_precision
         super().__init__(state_dict, device)
 
     def refresh(self):
@@ -284,6 +286,14 @@ class MithHashLayer(_HeadBase):
             self.keep.append(t)
             return t.data_ptr()
 
+        def split3(w):   # [out][in] fp32 -> bf16 [out][3*in] = [hi | lo | hi]
+            w = w.detach().to(device=self.device_, dtype=torch.float32)
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            t = torch.cat([hi, lo, hi], dim=1).contiguous()
+            self.keep.append(t)
+            return t.data_ptr()
+
         for m, g, t in (("img", "gcl_i.", "lct_i."), ("txt", "gcl_t.", "lct_t.")):
             h = MithHeadStruct()
             h.nbits, h.dim = sd[g + "common_concept_embedding.weight"].shape
@@ -293,6 +303,9 @@ class MithHashLayer(_HeadBase):
                 h.ln_gain[n], h.ln_bias[n] = f32(sd[g + "mlp.lns.%d.weight" % n]), f32(sd[g + "mlp.lns.%d.bias" % n])
                 h.w1[n], h.b1[n] = bf16(sd[g + "mlp.mlps.%d.0.weight" % n]), f32(sd[g + "mlp.mlps.%d.0.bias" % n])
                 h.w2[n], h.b2[n] = bf16(sd[g + "mlp.mlps.%d.3.weight" % n]), f32(sd[g + "mlp.mlps.%d.3.bias" % n])
+                if self.split_precision:
+                    h.w1_split[n] = split3(sd[g + "mlp.mlps.%d.0.weight" % n])
+                    h.w2_split[n] = split3(sd[g + "mlp.mlps.%d.3.weight" % n])
                 n += 1
             h.mlp_layers = n
             h.w_concept = f32(sd[g + "common_concept_embedding.weight"])

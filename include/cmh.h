@@ -194,6 +194,7 @@ int cmh_euclid_sim_f32(const float* a, int64_t n, const float* b, int64_t m, int
 #define CMH_EPI_F32 3        /* out fp32 = acc + bias                                   */
 #define CMH_EPI_TANH_F32 4   /* out fp32 = tanh(acc + bias)        (DSPH head)          */
 #define CMH_EPI_ERF_GELU_BF16 5 /* out bf16 = GELU_erf(acc + bias) (MITH residual MLPs, models/MITH/hash/hash.py:22) */
+#define CMH_EPI_ERF_GELU_F32 6  /* out fp32 = GELU_erf(acc + bias) (split-precision token path of the MITH head)     */
 int cmh_gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, int64_t N, int64_t ldw,
                   const float* bias, int epilogue, void* out, int64_t ldo, const float* resid, int64_t ldr,
                   void* stream);
@@ -318,6 +319,12 @@ typedef struct cmh_mith_head {
     const float* b1[CMH_MITH_MAX_MLP_LAYERS];
     const void*  w2[CMH_MITH_MAX_MLP_LAYERS];        /* gcl_*.mlp.mlps.<i>.3.weight [D][4D] bf16                            */
     const float* b2[CMH_MITH_MAX_MLP_LAYERS];
+    /* Optional split-precision copies for the TOKEN path (the one that feeds the discontinuous top-k concept selection):
+     * w = hi + lo with hi = bf16(w), lo = bf16(w - hi); w1_split = [hi | lo | hi] along K (bf16 [4D][3D]), w2_split likewise
+     * (bf16 [D][12D]).  With A split the same way ([hi | hi | lo]) one K-concatenated GEMM accumulates hi.hi + hi.lo + lo.hi:
+     * ~2^-16 relative instead of 2^-9.  NULL = plain bf16 (3x fewer FLOPs on the token MLPs). */
+    const void*  w1_split[CMH_MITH_MAX_MLP_LAYERS];
+    const void*  w2_split[CMH_MITH_MAX_MLP_LAYERS];
     const float* w_concept;                          /* gcl_*.common_concept_embedding.weight [K][D] fp32 (no bias)         */
     const float* pos;                                /* lct_*.position.pe[:, 0, :] [K][D] fp32                              */
     cmh_tower    transformer;                        /* lct_*.transformer: width, layers, heads, blocks (other fields unused) */

@@ -7,8 +7,12 @@ accumulation (same class as the CLIP towers).  cls_hash is a smoo
 DISCONTINUOUS: a similarity within bf16 noise of a token's k-th value switches that token on or off for a concept and moves
 the merged token by O(1/#selected tokens).  With K concepts spread over (0, 1) the gap between a token's 8th and 9th
 similarity is ~1/K, so at bf16 noise (~1e-2 relative) a few per cent of the (token, concept) decisions differ from an fp32
-evaluation, on random-normal token inputs more than on trained features.  Stated tolerance for tokens_hash: mean abs error
-<= 2e-2, at most 5 % of the entries off by more than 6e-2 ("selection flips"; 2.8 % observed at K = 64, 0 at K = 16).  Code bits: at most 3 % differ from the reference, and every differing bit either has a
+evaluation, on random-normal token inputs more than on trained features.  Therefore the head runs the token-path MLPs in
+SPLIT precision by default (operands and weights as bf16 hi + lo parts, K-concatenated GEMM: ~2^-16 relative): against the
+reference golden tokens_hash then agrees to max 3e-2 / mean 5e-3 with no selection flip.  With split_precision=False (plain
+bf16, 3x fewer FLOPs on those GEMMs) and for the end-to-end model (where the bf16 towers already perturb the token features)
+the stated tolerance is: mean abs error <= 2e-2, at most 5 % of the entries off by more than 6e-2 ("selection flips"; 2.8 %
+observed at K = 64, 0 at K = 16).  Code bits: at most 3 % differ from the reference, and every differing bit either has a
 reference margin |cls_hash + tokens_hash| < 0.1 or sits on a selection flip."""
 import os
 
@@ -43,6 +47,8 @@ def check_hash(got, want, what):
     err = np.abs(got - want)
     if what == "cls_hash":
         assert err.max() <= 6e-2 and err.mean() <= 1e-2, (what, err.max(), err.mean())
+    elif what == "tokens_hash_split":
+        assert err.max() <= 3e-2 and err.mean() <= 5e-3, (what, err.max(), err.mean())
     else:
         assert err.mean() <= 2e-2 and (err > 6e-2).mean() <= 0.05, (what, err.mean(), (err > 6e-2).mean())
     return err > 6e-2
@@ -58,9 +64,10 @@ def check_code(code, ref_sum, flips=None):
     assert not unexplained.any(), np.abs(ref_sum[unexplained])
 
 
+@pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("nbits", [16, 64])
-def test_mith_head_matches_reference_golden(nbits):
-    head = models.MithHashLayer(synth.mith_head_state_dict(512, nbits, seed=51), "cuda")
+def test_mith_head_matches_reference_golden(nbits, split):
+    head = models.MithHashLayer(synth.mith_head_state_dict(512, nbits, seed=51), "cuda", split_precision=split)
     for m in ("img", "txt"):
         cls, tokens, mask = inputs(5, 49, 61, False) if m == "img" else inputs(6, 32, 62, True)
         r = head.encode_img(cls.cuda(), tokens.cuda()) if m == "img" else head.encode_txt(cls.cuda(), tokens.cuda(), mask.cuda())
@@ -70,7 +77,7 @@ def test_mith_head_matches_reference_golden(nbits):
         cos = (res * Z[p + "res"]).sum(-1)
         assert cos.min() >= 0.9995, cos.min()
         check_hash(ch, Z[p + "cls_hash"], "cls_hash")
-        flips = check_hash(th, Z[p + "tok_hash"], "tokens_hash")
+        flips = check_hash(th, Z[p + "tok_hash"], "tokens_hash_split" if split else "tokens_hash")
         tcos = (trans * Z[p + "trans"]).sum(-1)          # both sides are unit vectors, [K, B]
         assert np.median(tcos) >= 0.999 and (tcos < 0.98).mean() <= 0.05, (np.median(tcos), (tcos < 0.98).mean())
         check_code(np.sign(ch + th), Z[p + "cls_hash"] + Z[p + "tok_hash"], flips)
