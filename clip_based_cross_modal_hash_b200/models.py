@@ -182,6 +182,15 @@ class _RegistryMixin:
     def to(self, *a, **k):
         return self
 
+    # models/base.py:57-63.  This path holds no trainable tensors (evaluation only): nothing to freeze.  BaseTrainer still
+    # builds its optimiser from `.backbone.parameters()` / `.hash.parameters()` (runners/base.py:134-136); those iterators
+    # are empty here, so a trainer that only evaluates should skip `build_optimizer` (torch refuses empty parameter lists).
+    def freezen(self):
+        return None
+
+    def unfreezen(self):
+        return None
+
 
 class _Model(_RegistryMixin, torch.nn.Module):
     HASH = None
@@ -237,6 +246,24 @@ def hyp_loss(x, y, label, proxies, threshold: float, alpha: float = 0.8) -> torc
 class DSPH(_Model):
     HASH = DsphHashLayer
     HEAD_INIT = "dsph_head_state_dict"
+
+    def __init__(self, clip_state_dict, hash_state_dict, device="cuda", proxies=None, threshold: float = 0.0, alpha: float = 0.8):
+        super().__init__(clip_state_dict, hash_state_dict, device)
+        self.proxies, self.threshold, self.alpha = proxies, threshold, alpha   # HyP(numclass, output_dim, ..., threshold)
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        if "hyp.proxies" in state_dict:                                       # models/DSPH/DSPH.py:33-35
+            self.proxies = state_dict["hyp.proxies"].detach().float()
+        return super().load_state_dict(state_dict, strict)
+
+    def object_function(self, img_hash, txt_hash, labels=None, indexs=None, **kwargs):
+        """models/DSPH/DSPH.py:78-82 -> (loss, loss_dict); the VALUE of the HyP objective only, no gradient."""
+        if self.proxies is None:
+            raise _lib.CmhError("DSPH.object_function needs the HyP proxies (a trained checkpoint's 'hyp.proxies')")
+        if labels is None:
+            labels = torch.eye(img_hash.shape[0], dtype=torch.int64)
+        loss = hyp_loss(img_hash, txt_hash, labels, self.proxies, self.threshold, self.alpha)
+        return loss, {"All loss": loss.data}
 
     @staticmethod
     def make_hash_code(code):               # runners/base.py:407-410 (in place, like the reference)
