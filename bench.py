@@ -446,7 +446,7 @@ def run_ours(args, cfg, name):
         # the bound SURVEY §8(d) names for this path: the POPC pipe (16 lanes/clk/SM), one popc.b32 per code word per pair and
         # per ranking pass (hist + rank = 2 passes)
         sm_clock = (line["clocks"].get("sm_mhz") or 1965.0) * 1e6
-        popc_peak = 16.0 * 148 * sm_clock
+        popc_peak = 16.0 * 148 * sm_clock   # measured 15.8 popc/clk/SM on this pool (scripts/micro/popc_peak.cu, profiles/README.md)
         passes_ms = stage["hist_kernel"] + stage[dom] if dom != "hist_kernel" else stage["hist_kernel"] + stage["rank_topk_kernel"]
         line["roofline"]["popc_bound"] = {"popc_per_step": 2 * Q * N * W, "peak_popc_per_s": popc_peak,
                                           "frac": (2.0 * Q * N * W / popc_peak) / (passes_ms * 1e-3),
