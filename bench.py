@@ -187,13 +187,14 @@ def cpu_encode_images_per_sec(n_images=512, chunk=32):
 
 
 def bench_encode(args, dev, world, rank, barrier, all_max):
-    """DSPH-style get_code step on random-init ViT-B/32: images -> CLIP tower -> hash head -> packed 64-bit codes."""
+    """get_code step of BASELINE's C2 method (DCMHT, 64 bit) on random-init ViT-B/32: images -> CLIP tower -> hash head ->
+    packed 64-bit codes."""
     from clip_based_cross_modal_hash_b200 import models
     from oracle import clip_port as port
 
     B = ENCODE_BATCH
     sd = synth.clip_state_dict(synth.VIT_B32, seed=0)
-    model = models.DSPH(sd, synth.dsph_head_state_dict(512, 64, seed=1), device=dev)
+    model = models.DCMHT(sd, synth.dcmht_head_state_dict(512, 64, seed=1), device=dev)
     nbuf = 3  # 3 x 154 MB of images > 126 MB L2: every step reads its batch from HBM
     host_img = [synth.random_images(B, seed=10 + i + 100 * rank).pin_memory() for i in range(nbuf)]
     text, _ = synth.random_captions(B, seed=20 + rank)
@@ -232,8 +233,8 @@ def bench_encode(args, dev, world, rank, barrier, all_max):
     ach = fl * B / (tower_ms * 1e-3) / 1e12
     out = {
         "metric": "clip_encode_images_per_sec", "value": B * world / (img_ms * 1e-3), "unit": "img/s", "batch_per_gpu": B,
-        "ms_per_batch": img_ms, "what": "DSPH get_code step: fp32 NCHW images (resident in HBM) -> ViT-B/32 tower (bf16 tcgen05 GEMMs, "
-        "fp32 residual stream) -> tanh head -> 64-bit packed codes; random-init weights, synthetic images",
+        "ms_per_batch": img_ms, "what": "DCMHT get_code step: fp32 NCHW images (resident in HBM) -> ViT-B/32 tower (bf16 tcgen05 GEMMs, "
+        "fp32 residual stream) -> DCMHT head (fp32) -> pair argmax -> 64-bit packed codes; random-init weights, synthetic images",
         "text": {"value": B * world / (txt_ms * 1e-3), "unit": "captions/s", "ms_per_batch": txt_ms, "tokens": 32},
         "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "image+caption pairs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 32 * 8 + B * 8, "d2h_bytes_per_step": int(codes_host.numel() * 4 // steps),
@@ -241,9 +242,9 @@ def bench_encode(args, dev, world, rank, barrier, all_max):
         "roofline": {"bound": "tensor", "kernel": "image tower (12 blocks, 50 tokens)", "achieved": ach, "peak": sustained,
                      "unit": "TFLOP/s", "frac": ach / sustained, "frac_of_burst_peak": ach / burst, "peak_kind": kind + " cuBLAS bf16, sustained",
                      "traffic": None, "algorithmic_flops_per_image": fl, "tower_ms": tower_ms},
-        "gpu_launches_per_step": 12 * 7 + 7,
+        "gpu_launches_per_step": 12 * 7 + 10,
         "l2": "3 image batches of 154 MB are cycled (462 MB > 126 MB L2): every step reads its images from HBM",
-        "gpu_launches": (12 * 7 + 7) * steps * 2 + (12 * 7 + 6) * steps,
+        "gpu_launches": (12 * 7 + 10) * steps * 2 + (12 * 7 + 10) * steps,
     }
     return out
 
