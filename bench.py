@@ -131,7 +131,7 @@ def run_reference(args, cfg, name):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    sample_q = min(cfg["Q"], 500)   # ~2 s of CPU work per step on 16 threads at C2
+    sample_q = max(50, min(cfg["Q"], int(5e7 // cfg["N"])))   # ~1.5 s of CPU work per step on 16 threads
     v, per = cpu_reference_pairs_per_sec(cfg, sample_q, args.steps, args.warmup)
     cores = torch.get_num_threads()
     line = {
@@ -454,7 +454,7 @@ def run_ours(args, cfg, name):
                                           "note": "fraction of the POPC-pipe bound reached by the two ranking passes together"}
         line["stage_ms"] = stage
         torch.set_num_threads(os.cpu_count() or 1)
-        sample_q = min(Q, 1500)   # ~10 s of CPU work (two passes: one warm-up, one timed)
+        sample_q = max(50, min(Q, int(2e8 // N)))   # ~6 s of CPU work per pass (one warm-up pass, one timed)
         v, per = cpu_reference_pairs_per_sec(cfg, sample_q, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "%d of %d queries x %d gallery items, %.1f s" % (sample_q, Q, N, per)}
