@@ -1,23 +1,31 @@
 #!/usr/bin/env python
-"""bench.py — the retrieval hot path (calc_map_k: pack -> hist -> scan -> rank -> mAP) on N GPUs of one node.
+"""bench.py — the Hamming-retrieval hot path on N GPUs of one node (the configuration north_star targets).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3|C4-64|...]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C4-64|C2|C3|...]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
          bench.py --gpus N --steps K --warmup W
 
-One JSON line on stdout (rank 0).  A "step" is one full evaluation of the workload: the reference-format
-inputs (+-1 fp32 codes, int64 multi-hot labels) are bit-packed, every query is ranked against the whole
-gallery and the mAP scalar is produced.  metric = query x gallery pairs per second.
+One JSON line on stdout (rank 0).
 
-  value   inputs resident in HBM when the clock starts (CUDA events, max over ranks, L2 flushed between steps)
-  e2e     the same through the reference-facing call calc_utils.calc_map_k(host tensors): pinned host buffers,
-          H2D copies and the D2H of the result inside the timed region
-  N > 1   weak scaling: every rank holds one gallery shard of the workload's size (total gallery = N x shard),
-          queries replicated; exchange (NCCL) = all-gather of per-shard bucket totals + AP partials (mAP) or bucket totals +
-          one all-reduce(MAX) of the [Q, k] key buffer (top-k; --topk-exchange allgather_merge = BASELINE's literal all-gather).
+Headline (default): workload C4-64 = BASELINE.json configs[3] at 64 bit — Hamming + per-query top-1000 of 10 000 queries
+against a FIXED 1 000 000-item gallery.  With N GPUs the gallery is split into N contiguous shards (STRONG scaling,
+`retrieval.shard_bounds`), queries replicated, one exchange step.  A "step" is one full evaluation: the
+reference-format inputs (+-1 fp32 codes) are bit-packed, every query is ranked against the whole gallery, the first k
+entries of the stable ranking come out as sorted (distance, index) keys on every rank.  metric = query x gallery pairs/s.
 
---impl reference times the reference's own CPU evaluator (oracle/calc_utils_port.py: the same ATen CPU ops as
-common/calc_utils.py, the Python reference itself cannot travel to the GPU box) on a bounded query sample.
+  value      inputs resident in HBM when the clock starts (CUDA events, max over ranks, L2 flushed between steps)
+  e2e        the same through the reference-facing call (calc_utils.hamming_topk / hamming_topk_sharded) on pinned HOST
+             tensors: H2D copies of codes and the D2H of the result inside the timed region
+  roofline   SURVEY.md §8(d): compulsory bytes N*W + Q*W + Q*k*8 against the measured HBM peak AND the integer bound
+             t_popc = Q*N*ceil(K/32) / (16 popc/clk/SM); graded figure max(t_hbm, t_popc) / t_measured
+  sweep      the same step at 16 / 32 / 128 bit (fewer timed steps)
+  c2_map     BASELINE.json configs[1]: calc_map_k on 5 000 x 117 000, 64 bit, 80 classes, full ranking (N > 1: one
+             workload-sized shard per rank, weak scaling)
+  encode     CLIP ViT-B/32 image encode at batch 256 per GPU (second half of BASELINE.json's metric)
+
+--impl reference times the reference's own CPU path for the same workload (oracle/calc_utils_port.py: the ATen CPU ops of
+common/calc_utils.py:51-56,76-77 — fp32 mm + torch.sort; the Python reference cannot travel to the GPU box) on a bounded
+query sample per step, all host threads.
 """
 from __future__ import annotations
 
@@ -40,19 +48,21 @@ from clip_based_cross_modal_hash_b200 import synth  # noqa: E402
 METRIC = "hamming_retrieval_query_x_gallery_pairs_per_sec"
 UNIT = "pairs/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)
+SM_COUNT = 148
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
+# captures (profiles/README.md names the file each number comes from); None = not captured for that kernel
+NCU_TRAFFIC = {}
 
 
-def peaks():
+def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        try:
-            with open(path) as f:
-                d = json.load(f)
-            if "hbm_gbs" in d:
-                return float(d["hbm_gbs"]), "measured"
-        except Exception:
-            pass
-    return FALLBACK_HBM_GBS, "fallback"
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm": float(d["hbm_gbs"]), "bf16_sustained": float(d["bf16_tflops_sustained"]),
+                "bf16_burst": float(d["bf16_tflops"]), "kind": "measured"}
+    except Exception:
+        return {"hbm": FALLBACK_HBM_GBS, "bf16_sustained": 1400.0, "bf16_burst": 1590.0, "kind": "fallback"}
 
 
 class ClockSampler:
@@ -78,7 +88,7 @@ class ClockSampler:
                     self.rows.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -100,30 +110,50 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_inputs(cfg, seed, n_items=None):
+def make_inputs(cfg, seed, n_items=None, labels=True):
     Q, N, K, C = cfg["Q"], n_items or cfg["N"], cfg["K"], cfg["C"]
-    return (synth.random_codes(Q, K, seed), synth.random_codes(N, K, seed + 1),
-            synth.random_labels(Q, C, seed + 2), synth.random_labels(N, C, seed + 3))
+    qB, rB = synth.random_codes(Q, K, seed), synth.random_codes(N, K, seed + 1)
+    if not labels:
+        return qB, rB, None, None
+    return qB, rB, synth.random_labels(Q, C, seed + 2), synth.random_labels(N, C, seed + 3)
 
 
 # ---------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference's CPU evaluator on a bounded query sample
+# reference arm / cpu baseline: the reference's CPU ops on a bounded query sample
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_pairs_per_sec(cfg, sample_q, steps, warmup):
+def cpu_reference_map(cfg, sample_q, steps, warmup):
     from oracle import calc_utils_port as port
 
     qB, rB, qL, rL = make_inputs(cfg, 1234)
     qB, qL = qB[:sample_q], qL[:sample_q]
-    k = cfg["k"]
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        port.calc_map_k(qB, rB, qL, rL, k, stable=False, query_chunk=100)  # as shipped: unstable sort
-        dt = time.perf_counter() - t0
+        port.calc_map_k(qB, rB, qL, rL, cfg["k"], stable=False, query_chunk=100)  # as shipped: unstable sort
         if it >= warmup:
-            times.append(dt)
+            times.append(time.perf_counter() - t0)
     per = sum(times) / len(times)
     return sample_q * cfg["N"] / per, per
+
+
+def cpu_reference_topk(cfg, sample_q, steps, warmup):
+    """calc_hammingDist + torch.sort (common/calc_utils.py:76-77, unstable as shipped), first k columns kept."""
+    from oracle import calc_utils_port as port
+
+    qB, rB, _, _ = make_inputs(cfg, 1234, labels=False)
+    qB = qB[:sample_q]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        port.hamming_rank_topk(qB, rB, cfg["k"], stable=False)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    per = sum(times) / len(times)
+    return sample_q * cfg["N"] / per, per
+
+
+def cpu_sample(cfg, op, budget_pairs):
+    return max(8, min(cfg["Q"], int(budget_pairs // cfg["N"])))
 
 
 def run_reference(args, cfg, name):
@@ -131,18 +161,23 @@ def run_reference(args, cfg, name):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    sample_q = max(50, min(cfg["Q"], int(5e7 // cfg["N"])))   # ~1.5 s of CPU work per step on 16 threads
-    v, per = cpu_reference_pairs_per_sec(cfg, sample_q, args.steps, args.warmup)
     cores = torch.get_num_threads()
+    if args.op == "topk":
+        sample_q = cpu_sample(cfg, "topk", 3.2e7)          # ~1 s of CPU work per step on 16 threads
+        v, per = cpu_reference_topk(cfg, sample_q, args.steps, args.warmup)
+        what = "calc_hammingDist + torch.sort (common/calc_utils.py:51-56,76-77), first %d columns" % cfg["k"]
+    else:
+        sample_q = cpu_sample(cfg, "map", 5e7)
+        v, per = cpu_reference_map(cfg, sample_q, args.steps, args.warmup)
+        what = "calc_map_k (common/calc_utils.py:58-92)"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "Q": cfg["Q"], "N": cfg["N"], "bits": cfg["K"], "classes": cfg["C"], "k": cfg["k"],
-                   "note": "reference CPU evaluator (torch CPU ops of common/calc_utils.py:58-92, restated in "
-                           "oracle/calc_utils_port.py), one step = %d queries x full gallery" % sample_q},
+        "config": workload_config(cfg, name, args.op, args.gpus, "strong"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d of %d queries x %d gallery items per step" % (sample_q, cfg["Q"], cfg["N"])},
+                         "sample": "%d of %d queries x %d gallery items per step; %s restated in oracle/calc_utils_port.py"
+                                   % (sample_q, cfg["Q"], cfg["N"], what)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -154,20 +189,291 @@ def run_reference(args, cfg, name):
     print(json.dumps(line), flush=True)
 
 
+def workload_config(cfg, name, op, world, scaling):
+    """Identical in both arms (the driver compares the `config` objects)."""
+    return {"workload": name, "Q": cfg["Q"], "N": cfg["N"], "bits": cfg["K"], "classes": cfg["C"] if op == "map" else None,
+            "k": cfg["k"], "op": op, "gallery": "fixed total, split over the GPUs" if scaling == "strong" else "one workload-sized shard per GPU"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# helpers of our arm
+# ---------------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def all_max(self, v):
+        t = torch.tensor([v] if not isinstance(v, (list, tuple)) else list(v), dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        out = t.tolist()
+        return out[0] if not isinstance(v, (list, tuple)) else out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def launches():
+    from clip_based_cross_modal_hash_b200 import _lib
+
+    return int(_lib.lib().cmh_launch_count())
+
+
+def survey_roofline(Q, N_local, K, k, t_ms, peaks, sm_mhz, op="topk", C=0):
+    """compulsory HBM bytes and single-pass POPC work of ONE GPU's share against the measured step time."""
+    Wb = K // 8 if K % 8 == 0 else (K + 7) // 8
+    bytes_c = N_local * Wb + Q * Wb + (Q * k * 8 if op == "topk" else (N_local + Q) * 16 + Q * (K + 1) * 4)
+    t_hbm = bytes_c / (peaks["hbm"] * 1e9) * 1e3
+    popc_peak = 16.0 * SM_COUNT * (sm_mhz or 1965.0) * 1e6
+    t_popc = Q * N_local * ((K + 31) // 32) / popc_peak * 1e3
+    return {"compulsory_bytes": bytes_c, "t_hbm_ms": t_hbm, "t_popc_ms": t_popc, "t_measured_ms": t_ms,
+            "popc_peak_per_s": popc_peak, "achieved": max(t_hbm, t_popc) / t_ms,
+            "definition": "max(t_hbm, t_popc) / t_measured; t_hbm = (N*W + Q*W + Q*k*8 bytes) / measured HBM peak, "
+                          "t_popc = Q*N*ceil(K/32) / (16 popc/clk/SM x 148 SMs x SM clock), per GPU, whole step incl. pack"}
+
+
+def check_topk_against_sort(R, keys, qp, gp_full, K, k, nq=64):
+    """Untimed parity check: first `nq` queries against torch.sort(stable) of the materialised XOR+popcount matrix."""
+    nq = min(nq, qp.shape[0])
+    hm = R.hamming_matrix(qp[:nq].contiguous(), gp_full, K)
+    vals, idx = torch.sort(hm, dim=-1, stable=True)
+    kk = min(k, gp_full.shape[0])
+    want = (vals[:, :kk].to(torch.int64) << 32) | idx[:, :kk]
+    got = keys[:nq, :kk]
+    return {"queries": nq, "against": "torch.sort(stable) of the materialised Hamming matrix of the FULL gallery",
+            "equal": bool(torch.equal(got, want))}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Hamming + top-k (C4), strong or weak scaling
+# ---------------------------------------------------------------------------------------------------------
+def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True, want_stage=True):
+    from clip_based_cross_modal_hash_b200 import calc_utils, retrieval as R
+
+    world, rank, dev = D.world, D.rank, D.dev
+    Q, N, K, k = cfg["Q"], cfg["N"], cfg["K"], cfg["k"]
+    qB, rB_full, _, _ = make_inputs(cfg, 1234, labels=False)
+    if scaling == "strong":
+        bounds = R.shard_bounds(N, world)
+        lo, hi = bounds[rank]
+        n_geom = max(b[1] - b[0] for b in bounds)
+        n_total = N
+        rB = rB_full[lo:hi].contiguous()
+    else:  # one workload-sized shard per rank
+        lo, hi, n_geom, n_total = rank * N, (rank + 1) * N, N, N * world
+        rB = rB_full if rank == 0 else synth.random_codes(N, K, 1234 + 1 + 7 * rank)
+    host_q, host_r = qB.pin_memory(), rB.pin_memory()
+    d_qB, d_rB = host_q.to(dev), host_r.to(dev)
+    st = R.CudaStages()
+    ev = R.ShardedEvaluator(stages=st) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    keys_buf = torch.empty((Q, k), dtype=torch.int64, device=dev)
+
+    def step(events=None):
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append(e)
+        mark()
+        qp, gp = R.pack_codes(d_qB), R.pack_codes(d_rB)
+        mark()
+        if world > 1:
+            keys = ev.topk(qp, gp, K, k, lo, n_geom=n_geom, method=args.topk_exchange)
+            mark()
+            return keys
+        keys = R.topk(qp, gp, K, k, stages=events, out=keys_buf)
+        mark()
+        return keys
+
+    for _ in range(max(warmup, 3)):
+        step()
+        flush.zero_()
+    D.barrier()
+    l0 = launches()
+    per_step, stage_ms = [], None
+    with ClockSampler(D.local_rank) as clocks:
+        D.barrier()
+        for _ in range(steps):
+            flush.zero_()
+            evs = []
+            keys = step(evs)
+            torch.cuda.synchronize()
+            per_step.append(evs[0].elapsed_time(evs[-1]))
+            if world == 1 and want_stage:
+                d = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]
+                stage_ms = d if stage_ms is None else [a + b for a, b in zip(stage_ms, d)]
+        D.barrier()
+    n_launch = launches() - l0
+    total_ms = D.all_max(sum(per_step))
+    out = {"bits": K, "ms_per_step": total_ms / steps, "value": Q * n_total * steps / (total_ms * 1e-3), "steps": steps,
+           "clocks": clocks.summary(), "gpu_launches": n_launch}
+
+    # untimed parity check of the last step's result (rank 0 holds the full gallery in strong mode)
+    if scaling == "strong" or world == 1:
+        gp_full = R.pack_codes(rB_full.to(dev))
+        chk = check_topk_against_sort(R, keys, R.pack_codes(d_qB), gp_full, K, k)
+        ok = D.all_max(0.0 if chk["equal"] else 1.0) == 0.0
+        chk["equal_on_every_rank"] = ok
+        out["parity_check"] = chk
+        del gp_full
+    if world == 1 and want_stage and stage_ms is not None:
+        names = R.TOPK_STAGE_NAMES[:len(stage_ms) - 1]
+        out["stage_ms"] = {"pack": stage_ms[0] / steps, **{n: v / steps for n, v in zip(names, stage_ms[1:])}}
+    n_local = hi - lo
+    out["survey_8d"] = survey_roofline(Q, n_local, K, k, out["ms_per_step"], peaks, out["clocks"].get("sm_mhz"))
+
+    if want_e2e:
+        pin_d = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+        pin_i = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+        e2e_ms = []
+        for it in range(2 + steps):
+            flush.zero_()
+            D.barrier()
+            t0 = time.perf_counter()
+            if world == 1:
+                calc_utils.hamming_topk(host_q, host_r, k, out=(pin_d, pin_i))
+            else:
+                calc_utils.hamming_topk_sharded(host_q, host_r, k, lo, n_geom, evaluator=ev, method=args.topk_exchange,
+                                                out=(pin_d, pin_i) if rank == 0 else None, return_keys=rank != 0)
+            torch.cuda.synchronize()
+            if it >= 2:
+                e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        D.barrier()
+        tot = D.all_max(sum(e2e_ms))
+        med = D.all_max(statistics.median(e2e_ms))
+        h2d = host_q.numel() * 4 + host_r.numel() * 4
+        out["e2e"] = {"value": Q * n_total * len(e2e_ms) / (tot * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": Q * k * 12, "ms_per_step": tot / len(e2e_ms), "ms_per_step_median": med,
+                      "what": "calc_utils.hamming_topk%s(pinned host +-1 fp32 codes) -> (dist fp32, index int64) in pinned host "
+                              "memory%s" % ("_sharded" if world > 1 else "", " on rank 0 (every rank holds the keys on its GPU)" if world > 1 else "")}
+    del d_qB, d_rB, flush, keys_buf
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# calc_map_k (C2 / C3)
+# ---------------------------------------------------------------------------------------------------------
+def bench_map(args, D, cfg, name, steps, warmup, peaks, want_cpu=True):
+    from clip_based_cross_modal_hash_b200 import calc_utils, retrieval as R
+
+    world, rank, dev = D.world, D.rank, D.dev
+    Q, N, K, C, k = cfg["Q"], cfg["N"], cfg["K"], cfg["C"], cfg["k"]
+    qB, rB, qL, rL = make_inputs(cfg, 1234 + 7 * rank)
+    if world > 1:
+        qB, _, qL, _ = make_inputs(cfg, 1234)  # queries replicated, one workload-sized gallery shard per rank (weak)
+    host = [t.pin_memory() for t in (qB, rB, qL, rL)]
+    d_qB, d_rB, d_qL, d_rL = (t.to(dev) for t in host)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    st = R.CudaStages()
+    ev = R.ShardedEvaluator(stages=st) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(events=None):
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append(e)
+        mark()
+        bad = R.new_bad_counter(dev)
+        qp, gp = R.pack_codes(d_qB, bad), R.pack_codes(d_rB, bad)
+        qlp, glp = R.pack_labels(d_qL, bad), R.pack_labels(d_rL, bad)
+        mark()
+        if world > 1:
+            res = ev.map_k(qp, qlp, gp, glp, K, C, k, n_geom=N)
+        else:
+            res = R.map_k(qp, qlp, gp, glp, K, C, k, stages=events)
+        mark()
+        return res.map
+
+    def e2e_step():
+        if world == 1:
+            return calc_utils.calc_map_k(host[0], host[1], host[2], host[3], k)
+        qp = R.pack_codes(host[0].to(dev, non_blocking=True))
+        gp = R.pack_codes(host[1].to(dev, non_blocking=True))
+        qlp = R.pack_labels(host[2].to(dev, non_blocking=True))
+        glp = R.pack_labels(host[3].to(dev, non_blocking=True))
+        return ev.map_k(qp, qlp, gp, glp, K, C, k, n_geom=N).map.cpu()
+
+    for _ in range(max(warmup, 3)):
+        step()
+        flush.zero_()
+    D.barrier()
+    l0 = launches()
+    per_step, stage_ms = [], None
+    with ClockSampler(D.local_rank) as clocks:
+        D.barrier()
+        for _ in range(steps):
+            flush.zero_()
+            evs = []
+            m = step(evs)
+            torch.cuda.synchronize()
+            per_step.append(evs[0].elapsed_time(evs[-1]))
+            if world == 1:
+                d = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]
+                stage_ms = d if stage_ms is None else [a + b for a, b in zip(stage_ms, d)]
+        D.barrier()
+        n_launch = launches() - l0
+        e2e_ms = []
+        for it in range(2 + steps):
+            flush.zero_()
+            D.barrier()
+            t0 = time.perf_counter()
+            e2e_step()
+            torch.cuda.synchronize()
+            if it >= 2:
+                e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        D.barrier()
+    total_ms = D.all_max(sum(per_step))
+    e2e_tot = D.all_max(sum(e2e_ms))
+    out = {"workload": name, "op": "map", "scaling": "weak" if world > 1 else "n/a", "Q": Q, "N_per_gpu": N, "bits": K, "classes": C,
+           "k": k, "ms_per_step": total_ms / steps, "value": Q * N * world * steps / (total_ms * 1e-3), "unit": UNIT,
+           "map": float(m.item()), "clocks": clocks.summary(), "gpu_launches": n_launch,
+           "e2e": {"value": Q * N * world * len(e2e_ms) / (e2e_tot * 1e-3), "unit": UNIT, "ms_per_step": e2e_tot / len(e2e_ms),
+                   "ms_per_step_median": D.all_max(statistics.median(e2e_ms)), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                   "what": "calc_utils.calc_map_k(pinned host +-1 fp32 codes, int64 labels) -> 0-dim fp32 CPU tensor"}}
+    if world == 1:
+        names = ["pack"] + list(R.MAP_STAGE_NAMES)
+        out["stage_ms"] = {n: v / steps for n, v in zip(names, stage_ms)}
+        out["survey_8d"] = survey_roofline(Q, N, K, 0, out["ms_per_step"], peaks, out["clocks"].get("sm_mhz"), op="map", C=C)
+        # parity mode (bit-identical fp32 to the reference's reduction): cost of the same call
+        t0 = time.perf_counter()
+        mp = calc_utils.calc_map_k(host[0], host[1], host[2], host[3], k, mode="parity")
+        torch.cuda.synchronize()
+        out["parity_mode"] = {"ms": (time.perf_counter() - t0) * 1e3, "map_fp32": float(mp),
+                              "abs_diff_vs_device_mode": abs(float(mp) - float(torch.tensor(out["map"], dtype=torch.float64).to(torch.float32)))}
+        if want_cpu and rank == 0:
+            torch.set_num_threads(os.cpu_count() or 1)
+            sample_q = cpu_sample(cfg, "map", 1e8)
+            v, per = cpu_reference_map(cfg, sample_q, 1, 1)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": "%d of %d queries x %d gallery items, %.1f s" % (sample_q, Q, N, per)}
+    del d_qB, d_rB, d_qL, d_rL, flush
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 # CLIP ViT-B/32 encode (second half of BASELINE.json's metric: imgs/sec), batch 256 per GPU
 # ---------------------------------------------------------------------------------------------------------
 ENCODE_BATCH = 256
-
-
-def tensor_peak():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    try:
-        with open(path) as f:
-            d = json.load(f)
-        return float(d["bf16_tflops_sustained"]), float(d["bf16_tflops"]), "measured"
-    except Exception:
-        return 1400.0, 1590.0, "fallback"
 
 
 def cpu_encode_images_per_sec(n_images=512, chunk=32):
@@ -186,12 +492,52 @@ def cpu_encode_images_per_sec(n_images=512, chunk=32):
     return n_images / dt, dt
 
 
-def bench_encode(args, dev, world, rank, barrier, all_max):
+def reference_cuda_encode(dev, sd, d_img, iters=5):
+    """The bar SURVEY §2b names for the encoder: the reference's OWN PyTorch forward on the same B200 (cuBLAS/ATen kernels,
+    no code of this repo).  oracle/clip_port.py restates models/CLIP/model.py:232-268 op for op (the reference package cannot
+    travel to the GPU box); timed in fp32 (torch's default: no TF32), with TF32 matmuls, and under bf16 autocast."""
+    from oracle import clip_port as port
+
+    sd_dev = {k: v.to(dev) for k, v in sd.items() if k.startswith("visual.")}
+    out = {}
+
+    def timed(fn):
+        with torch.no_grad():
+            fn()
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(iters):
+                fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    nb = len(d_img)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        out["fp32_ms"] = timed(lambda i=0: port.encode_image(sd_dev, d_img[i % nb]))
+        torch.backends.cuda.matmul.allow_tf32 = True
+        out["tf32_ms"] = timed(lambda i=0: port.encode_image(sd_dev, d_img[i % nb]))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+    def bf16(i=0):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return port.encode_image(sd_dev, d_img[i % nb])
+    out["bf16_autocast_ms"] = timed(bf16)
+    return out
+
+
+def bench_encode(args, D, peaks):
     """get_code step of BASELINE's C2 method (DCMHT, 64 bit) on random-init ViT-B/32: images -> CLIP tower -> hash head ->
     packed 64-bit codes."""
     from clip_based_cross_modal_hash_b200 import models
-    from oracle import clip_port as port
+    from oracle import clip_port as port  # flops_image(): a constant
 
+    dev, world, rank = D.dev, D.world, D.rank
     B = ENCODE_BATCH
     sd = synth.clip_state_dict(synth.VIT_B32, seed=0)
     model = models.DCMHT(sd, synth.dcmht_head_state_dict(512, 64, seed=1), device=dev)
@@ -203,53 +549,72 @@ def bench_encode(args, dev, world, rank, barrier, all_max):
     d_txt = host_txt.to(dev)
     steps, warm = args.steps, max(args.warmup, 3)
 
-    def timed(fn, n):
-        barrier()
+    def one(fn, i):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(n):
-            fn(i)
+        fn(i)
         e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1)
+        return e0, e1
 
+    fns = {"img": lambda i: model.encode_image_packed(d_img[i % nbuf]),
+           "txt": lambda i: model.encode_text_packed(d_txt),
+           "tower": lambda i: model.backbone.encode_image(d_img[i % nbuf])}
     for i in range(warm):
-        model.encode_image_packed(d_img[i % nbuf])
-        model.encode_text_packed(d_txt)
-    img_ms = all_max(timed(lambda i: model.encode_image_packed(d_img[i % nbuf]), steps)) / steps
-    txt_ms = all_max(timed(lambda i: model.encode_text_packed(d_txt), steps)) / steps
-    # the image tower alone (without head/pack) for the tensor-pipe roofline
-    tower_ms = all_max(timed(lambda i: model.backbone.encode_image(d_img[i % nbuf]), steps)) / steps
+        for f in fns.values():
+            f(i)
+    D.barrier()
+    l0 = launches()
+    fns["img"](0)
+    per_image_batch = launches() - l0
+    # the three timed sections are INTERLEAVED step by step so clock / thermal drift hits them equally
+    evs = {n: [] for n in fns}
+    D.barrier()
+    for i in range(steps):
+        for n, f in fns.items():
+            evs[n].append(one(f, i))
+    torch.cuda.synchronize()
+    ms = {n: D.all_max(sum(a.elapsed_time(b) for a, b in evs[n])) / steps for n in fns}
     # end to end: models.get_code over host (pinned) batches, H2D inside the timed region, packed codes read back
-    loader = [(host_img[i % nbuf], host_txt, None, None, torch.arange(B) + B * i) for i in range(steps)]
-    models.get_code(model, loader[:2], 2 * B, dev)
+    nb_e2e = max(steps, 8)
+    loader = [(host_img[i % nbuf], host_txt, None, None, torch.arange(B) + B * i) for i in range(nb_e2e)]
+    models.get_code(model, loader[:3], 3 * B, dev)
     e2e_runs = []
-    for _ in range(2):   # two passes over the same `steps` batches, the faster one is reported (host-side jitter on shared boxes)
-        barrier()
+    for _ in range(5):
+        D.barrier()
         t0 = time.perf_counter()
-        ci, ct = models.get_code(model, loader, steps * B, dev)
+        ci, ct = models.get_code(model, loader, nb_e2e * B, dev)
         codes_host = ci.cpu()
-        e2e_runs.append(all_max((time.perf_counter() - t0) * 1e3) / steps)
-    e2e_ms = min(e2e_runs)
-    sustained, burst, kind = tensor_peak()
+        e2e_runs.append(D.all_max((time.perf_counter() - t0) * 1e3) / nb_e2e)
+    e2e_ms = statistics.median(e2e_runs)
     fl = port.flops_image()
-    ach = fl * B / (tower_ms * 1e-3) / 1e12
+    ach = fl * B / (ms["tower"] * 1e-3) / 1e12
     out = {
-        "metric": "clip_encode_images_per_sec", "value": B * world / (img_ms * 1e-3), "unit": "img/s", "batch_per_gpu": B,
-        "ms_per_batch": img_ms, "what": "DCMHT get_code step: fp32 NCHW images (resident in HBM) -> ViT-B/32 tower (bf16 tcgen05 GEMMs, "
+        "metric": "clip_encode_images_per_sec", "value": B * world / (ms["img"] * 1e-3), "unit": "img/s", "batch_per_gpu": B,
+        "ms_per_batch": ms["img"], "what": "DCMHT get_code step: fp32 NCHW images (resident in HBM) -> ViT-B/32 tower (bf16 tcgen05 GEMMs, "
         "fp32 residual stream) -> DCMHT head (fp32) -> pair argmax -> 64-bit packed codes; random-init weights, synthetic images",
-        "text": {"value": B * world / (txt_ms * 1e-3), "unit": "captions/s", "ms_per_batch": txt_ms, "tokens": 32},
+        "text": {"value": B * world / (ms["txt"] * 1e-3), "unit": "captions/s", "ms_per_batch": ms["txt"], "tokens": 32},
         "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "image+caption pairs/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 32 * 8 + B * 8, "d2h_bytes_per_step": int(codes_host.numel() * 4 // steps),
-                "what": "models.get_code over pinned host batches (image + caption), copies overlapped on a side stream; best of 2 passes",
+                "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 32 * 8 + B * 8, "d2h_bytes_per_step": int(codes_host.numel() * 4 // nb_e2e),
+                "what": "models.get_code over pinned host batches (image + caption), copies overlapped on a side stream; median of 5 passes of %d batches" % nb_e2e,
                 "ms_per_step_runs": e2e_runs},
-        "roofline": {"bound": "tensor", "kernel": "image tower (12 blocks, 50 tokens)", "achieved": ach, "peak": sustained,
-                     "unit": "TFLOP/s", "frac": ach / sustained, "frac_of_burst_peak": ach / burst, "peak_kind": kind + " cuBLAS bf16, sustained",
-                     "traffic": None, "algorithmic_flops_per_image": fl, "tower_ms": tower_ms},
-        "gpu_launches_per_step": 12 * 7 + 10,
+        "roofline": {"bound": "tensor", "kernel": "image tower (12 blocks, 50 tokens)", "achieved": ach, "peak": peaks["bf16_sustained"],
+                     "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"], "frac_of_burst_peak": ach / peaks["bf16_burst"],
+                     "peak_kind": peaks["kind"] + " cuBLAS bf16, sustained", "traffic": None, "algorithmic_flops_per_image": fl,
+                     "tower_ms": ms["tower"], "timing": "image / text / tower sections interleaved step by step"},
+        "gpu_launches_per_image_batch": per_image_batch,
         "l2": "3 image batches of 154 MB are cycled (462 MB > 126 MB L2): every step reads its images from HBM",
-        "gpu_launches": (12 * 7 + 10) * steps * 2 + (12 * 7 + 10) * steps,
     }
+    if rank == 0 and world == 1:
+        try:
+            ref = reference_cuda_encode(dev, sd, d_img)
+            ref["what"] = ("the reference's own PyTorch forward on this GPU (oracle/clip_port.py = models/CLIP/model.py:232-268 op for op, "
+                           "ATen/cuBLAS kernels), batch %d image tower" % B)
+            ref["speedup_vs_fp32"] = ref["fp32_ms"] / ms["tower"]
+            ref["speedup_vs_tf32"] = ref["tf32_ms"] / ms["tower"]
+            ref["speedup_vs_bf16_autocast"] = ref["bf16_autocast_ms"] / ms["tower"]
+            out["reference_cuda"] = ref
+        except Exception as e:  # a baseline leg must never take the bench line down
+            out["reference_cuda"] = {"error": repr(e)[:200]}
     return out
 
 
@@ -257,218 +622,110 @@ def bench_encode(args, dev, world, rank, barrier, all_max):
 # our arm
 # ---------------------------------------------------------------------------------------------------------
 def run_ours(args, cfg, name):
-    import torch.distributed as dist
-
-    from clip_based_cross_modal_hash_b200 import calc_utils, retrieval as R
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (the product has no CPU path); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    Q, N, K, C, k = cfg["Q"], cfg["N"], cfg["K"], cfg["C"], cfg["k"]
+    D = Dist()
+    peaks = load_peaks()
+    steps, warmup = args.steps, max(args.warmup, 3)
+    l_start = launches()
+    scaling = args.scaling
 
-    # reference-format inputs: this rank's gallery shard (weak scaling: one workload-sized shard per rank)
-    qB, rB, qL, rL = make_inputs(cfg, 1234 + 7 * rank)
-    if world > 1:
-        qB, _, qL, _ = make_inputs(cfg, 1234)  # queries replicated
-    host = [t.pin_memory() for t in (qB, rB, qL, rL)]
-    d_qB, d_rB, d_qL, d_rL = (t.to(dev) for t in host)
-    if k is None and args.op == "topk":
-        raise SystemExit("top-k needs a workload with k")
     if args.op == "topk":
-        host = host[:2]
-    h2d = sum(t.numel() * t.element_size() for t in host)
-    pinned_keys = torch.empty((Q, k), dtype=torch.int64).pin_memory() if args.op == "topk" else None
+        head = bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling)
+    else:
+        head = bench_map(args, D, cfg, name, steps, warmup, peaks)
 
-    st = R.CudaStages()
-    ev = R.ShardedEvaluator(stages=st) if world > 1 else None
-    plan = st.make_plan(Q, N, K, C)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    keys_buf = torch.empty((Q, k), dtype=torch.int64, device=dev) if args.op == "topk" else None
-
-    def step(events=None):
-        """pack + evaluate; returns the fp64 mAP (device).  events: optional list collecting stage boundaries."""
-        def mark():
-            if events is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                events.append(e)
-        mark()
-        bad = R.new_bad_counter(dev)
-        qp, gp = R.pack_codes(d_qB, bad), R.pack_codes(d_rB, bad)
-        if args.op == "topk":
-            mark()
-            if world > 1:
-                keys = ev.topk(qp, gp, K, k, rank * N, n_geom=N, method=args.topk_exchange)
-                mark()
-                return keys
-            pl = st.make_plan(Q, N, K, 0)
-            hist = st.hist(pl, qp, None, gp, None)
-            mark()
-            sc = st.scan(pl, hist, 1, 0, k, with_rel=False)
-            mark()
-            keys = st.rank_topk(pl, qp, gp, sc, k, 0, keys=keys_buf)
-            mark()
-            mark()
-            return keys
-        qlp, glp = R.pack_labels(d_qL, bad), R.pack_labels(d_rL, bad)
-        mark()
-        if world > 1:
-            res = ev.map_k(qp, qlp, gp, glp, K, C, k, n_geom=N)
-            mark()
-            return res.map
-        hist = st.hist(plan, qp, qlp, gp, glp)
-        mark()
-        sc = st.scan(plan, hist, 1, 0, k)
-        mark()
-        app = st.rank_map(plan, qp, qlp, gp, glp, sc)
-        mark()
-        _, m = st.map_finish(plan, app, sc["total"])
-        mark()
-        return m
-
-    def e2e_step():
-        if args.op == "topk":
-            qp = R.pack_codes(host[0].to(dev, non_blocking=True))
-            gp = R.pack_codes(host[1].to(dev, non_blocking=True))
-            keys = ev.topk(qp, gp, K, k, rank * N, n_geom=N, method=args.topk_exchange) if world > 1 else R.topk(qp, gp, K, k)
-            return pinned_keys.copy_(keys)
-        if world == 1:
-            return calc_utils.calc_map_k(host[0], host[1], host[2], host[3], k)
-        qp = R.pack_codes(host[0].to(dev, non_blocking=True))
-        gp = R.pack_codes(host[1].to(dev, non_blocking=True))
-        qlp = R.pack_labels(host[2].to(dev, non_blocking=True))
-        glp = R.pack_labels(host[3].to(dev, non_blocking=True))
-        return ev.map_k(qp, qlp, gp, glp, K, C, k, n_geom=N).map.cpu()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-        flush.zero_()
-    barrier()
-
-    stage_ms = None
-    per_step = []
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        for _ in range(args.steps):
-            flush.zero_()
-            evs = []
-            step(evs)
-            torch.cuda.synchronize()
-            per_step.append(evs[0].elapsed_time(evs[-1]))
-            if world == 1:
-                d = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]
-                stage_ms = d if stage_ms is None else [a + b for a, b in zip(stage_ms, d)]
-        barrier()
-        total_ms = sum(per_step)
-        # end-to-end through the public call, host buffers, copies inside the timed region
-        e2e_ms = []
-        for it in range(2 + args.steps):
-            flush.zero_()
-            barrier()
-            t0 = time.perf_counter()
-            out = e2e_step()
-            torch.cuda.synchronize()
-            if it >= 2:
-                e2e_ms.append((time.perf_counter() - t0) * 1e3)
-        barrier()
-    t = torch.tensor([total_ms, sum(e2e_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_total_ms = t.tolist()
-    pairs_per_step = Q * N * world
-    value = pairs_per_step * args.steps / (total_ms * 1e-3)
-    e2e_value = pairs_per_step * len(e2e_ms) / (e2e_total_ms * 1e-3)
-
-    def all_max(v):
-        tt = torch.tensor([v], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
-
+    sweep, c2 = None, None
+    if args.op == "topk" and not args.no_sweep:
+        sweep = []
+        for other in ("C4-16", "C4-32", "C4-128"):
+            if other == name:
+                continue
+            r = bench_topk(args, D, synth.CONFIGS[other], other, min(steps, 5), 3, peaks, scaling, want_e2e=False, want_stage=False)
+            sweep.append({"workload": other, "bits": r["bits"], "ms_per_step": r["ms_per_step"], "value": r["value"],
+                          "parity_check": r.get("parity_check"), "survey_8d": r["survey_8d"]})
+    if args.op == "topk" and not args.no_c2:
+        c2 = bench_map(args, D, synth.CONFIGS["C2"], "C2", min(steps, 10), 3, peaks, want_cpu=False)
     encode = None
     if not args.no_encode:
-        del d_qB, d_rB, d_qL, d_rL, flush
-        torch.cuda.empty_cache()
-        with ClockSampler(local_rank) as enc_clocks:
-            encode = bench_encode(args, dev, world, rank, barrier, all_max)
+        with ClockSampler(D.local_rank) as enc_clocks:
+            encode = bench_encode(args, D, peaks)
         encode["clocks"] = enc_clocks.summary()
+    total_launches = launches() - l_start
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+    if D.rank != 0:
+        D.close()
         return
 
-    peak, peak_kind = peaks()
+    world = D.world
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32", "data": "synthetic",
-        "config": {"workload": name, "Q": Q, "N_per_gpu": N, "N_total": N * world, "bits": K, "classes": C, "k": k,
-                   "step": "pack(+-1 fp32 codes, int64 labels) -> hist -> scan -> rank/AP -> mAP",
-                   "l2": "256 MiB flush write between timed steps", "op": args.op,
-                   "topk_exchange": args.topk_exchange if (args.op == "topk" and world > 1) else None, "map": float(out.item()) if (out is not None and args.op == "map") else None},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16 if args.op == "map" else Q * k * 8,
-                "ms_per_step": e2e_total_ms / len(e2e_ms)},
-        "gpu_launches": args.steps * 10,
-        "clocks": clocks.summary(),
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": scaling if args.op == "topk" else ("weak" if world > 1 else "strong"),
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(cfg, name, args.op, world, scaling if args.op == "topk" else "weak"),
+        "e2e": head["e2e"], "gpu_launches": total_launches, "clocks": head["clocks"],
+        "l2": "256 MiB flush write between timed steps",
     }
+    if args.op == "topk":
+        line["exchange"] = args.topk_exchange if world > 1 else None
+        line["parity_check"] = head.get("parity_check")
+        dom, dom_ms = None, None
+        if "stage_ms" in head:
+            line["stage_ms"] = head["stage_ms"]
+            dom, dom_ms = max(((n, v) for n, v in head["stage_ms"].items()), key=lambda x: x[1])
+        s8 = head["survey_8d"]
+        kern_ms = dom_ms if dom_ms is not None else head["ms_per_step"]
+        ach = s8["compulsory_bytes"] / (kern_ms * 1e-3) / 1e9
+        line["roofline"] = {
+            "bound": "hbm", "kernel": dom or "whole step (N > 1: stages not timed separately)", "achieved": ach, "peak": peaks["hbm"],
+            "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": NCU_TRAFFIC.get(dom), "peak_kind": peaks["kind"],
+            "kernel_ms": kern_ms, "share_of_step": kern_ms / head["ms_per_step"],
+            "algorithmic_bytes_per_launch": s8["compulsory_bytes"],
+            "note": "compulsory bytes (SURVEY 8(d): N*W + Q*W + Q*k*8) over the dominant kernel's time; the path never materialises "
+                    "Q x N, so it is bound by per-pair work on the SM (tensor pipe + counting epilogue), not by HBM: the graded figure "
+                    "is survey_8d.achieved",
+            "survey_8d": s8,
+        }
+    else:
+        line["stage_ms"] = head.get("stage_ms")
+        line["map"] = head["map"]
+        s8 = head.get("survey_8d")
+        if s8:
+            dom, dom_ms = max(((n, v) for n, v in head["stage_ms"].items()), key=lambda x: x[1])
+            ach = s8["compulsory_bytes"] / (dom_ms * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                                "traffic": NCU_TRAFFIC.get(dom), "peak_kind": peaks["kind"], "kernel_ms": dom_ms,
+                                "share_of_step": dom_ms / head["ms_per_step"], "algorithmic_bytes_per_launch": s8["compulsory_bytes"], "survey_8d": s8}
+        if "parity_mode" in head:
+            line["parity_mode"] = head["parity_mode"]
+    if sweep is not None:
+        line["sweep"] = sweep
+    if c2 is not None:
+        line["c2_map"] = c2
     if encode is not None:
         line["encode"] = encode
-        line["gpu_launches"] += encode["gpu_launches"]
     if world == 1:
-        names = (["pack", "hist_kernel", "scan", "rank_map_kernel", "map_finish"] if args.op == "map"
-                 else ["pack", "hist_kernel", "scan", "rank_topk_kernel", "none"])
-        stage = {n: v / args.steps for n, v in zip(names, stage_ms)}
-        W, LW = plan.W, plan.LW
-        # algorithmic bytes of the dominant kernel (rank_map): gallery codes+labels once, query codes+labels,
-        # rank bases in (within + below, all + rel), AP partials out   (DESIGN.md §5)
-        alg = (N * (W + LW) * 4 + Q * (W + LW) * 4 + 2 * plan.within_elems * 4 + 2 * plan.below_elems * 4
-               + Q * 4 + plan.ap_elems * 8)
-        dom = "rank_map_kernel"
-        if args.op == "topk":  # dominant = pass 1; compulsory bytes: gallery + query codes in, histograms out
-            dom = "hist_kernel"
-            alg = N * W * 4 + Q * W * 4 + plan.Qpad * (K + 1) * 4 * st.make_plan(Q, N, K, 0).nchunks
-        achieved = alg / (stage[dom] * 1e-3) / 1e9
-        line["roofline"] = {
-            "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg,
-            "kernel_ms": stage[dom], "share_of_step": stage[dom] / (total_ms / args.steps),
-            "note": "the ranking kernels keep the gallery in L2/shared memory and never materialise Q x N; they are "
-                    "bound by the integer/LSU issue rate (XOR+POPC+2 shared-memory counter updates per pair), not by HBM",
-            "pairs_per_sec_kernel": Q * N / (stage[dom] * 1e-3),
-        }
-        # the bound SURVEY §8(d) names for this path: the POPC pipe (16 lanes/clk/SM), one popc.b32 per code word per pair and
-        # per ranking pass (hist + rank = 2 passes)
-        sm_clock = (line["clocks"].get("sm_mhz") or 1965.0) * 1e6
-        popc_peak = 16.0 * 148 * sm_clock   # measured 15.8 popc/clk/SM on this pool (scripts/micro/popc_peak.cu, profiles/README.md)
-        passes_ms = stage["hist_kernel"] + stage[dom] if dom != "hist_kernel" else stage["hist_kernel"] + stage["rank_topk_kernel"]
-        line["roofline"]["popc_bound"] = {"popc_per_step": 2 * Q * N * W, "peak_popc_per_s": popc_peak,
-                                          "frac": (2.0 * Q * N * W / popc_peak) / (passes_ms * 1e-3),
-                                          "note": "fraction of the POPC-pipe bound reached by the two ranking passes together"}
-        line["stage_ms"] = stage
         torch.set_num_threads(os.cpu_count() or 1)
-        sample_q = max(50, min(Q, int(2e8 // N)))   # ~6 s of CPU work per pass (one warm-up pass, one timed)
-        v, per = cpu_reference_pairs_per_sec(cfg, sample_q, 1, 1)
+        if args.op == "topk":
+            sample_q = cpu_sample(cfg, "topk", 2.56e8)   # ~10 s of CPU work
+            v, per = cpu_reference_topk(cfg, sample_q, 1, 1)
+        else:
+            sample_q = cpu_sample(cfg, "map", 2e8)
+            v, per = cpu_reference_map(cfg, sample_q, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "%d of %d queries x %d gallery items, %.1f s" % (sample_q, Q, N, per)}
+                                "sample": "%d of %d queries x %d gallery items, %.1f s" % (sample_q, cfg["Q"], cfg["N"], per)}
+        if c2 is not None:
+            sq = cpu_sample(synth.CONFIGS["C2"], "map", 1e8)
+            v2, per2 = cpu_reference_map(synth.CONFIGS["C2"], sq, 1, 1)
+            c2["cpu_baseline"] = {"value": v2, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                  "sample": "%d of 5000 queries x 117000 gallery items, %.1f s" % (sq, per2)}
         if encode is not None:
             iv, idt = cpu_encode_images_per_sec()
             encode["cpu_baseline"] = {"value": iv, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
                                       "sample": "512 images (batches of 32) through the fp32 CPU restatement of encode_image, %.1f s" % idt}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 def main():
@@ -477,15 +734,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(synth.CONFIGS))
-    ap.add_argument("--topk-exchange", default="rank_scatter", choices=["rank_scatter", "allgather_merge"])
+    ap.add_argument("--workload", default="C4-64", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="top-k only: strong = the workload's gallery split over the GPUs (default), weak = one full gallery per GPU")
+    ap.add_argument("--topk-exchange", default="auto", choices=["auto", "peer_scatter", "rank_scatter", "allgather_merge"])
     ap.add_argument("--no-encode", action="store_true", help="skip the CLIP encode section of the line")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 16/32/128-bit sweep")
+    ap.add_argument("--no-c2", action="store_true", help="skip the C2 mAP object")
     ap.add_argument("--op", default=None, choices=["map", "topk"],
-                    help="map = calc_map_k (default for C1-C3); topk = Hamming + per-query top-k (default for C4-*)")
+                    help="topk = Hamming + per-query top-k (default for C4-*); map = calc_map_k (default for C1-C3)")
     args = ap.parse_args()
     if args.op is None:
         args.op = "topk" if args.workload.startswith("C4") else "map"
     cfg = synth.CONFIGS[args.workload]
+    if args.op == "topk" and cfg["k"] is None:
+        raise SystemExit("top-k needs a workload with k")
     if args.impl == "reference":
         run_reference(args, cfg, args.workload)
     else:

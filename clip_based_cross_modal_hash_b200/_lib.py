@@ -78,6 +78,7 @@ _PP = ctypes.POINTER(Plan)
 PROTOTYPES = {
     "cmh_abi_version": [],
     "cmh_last_error": [],
+    "cmh_launch_count": [],
     "cmh_device_info": [ctypes.POINTER(_i32)] * 3,
     "cmh_code_words": [_i32],
     "cmh_label_words": [_i32],
@@ -92,6 +93,7 @@ PROTOTYPES = {
     "cmh_hist_totals": [_PP, _vp, _vp, _vp],
     "cmh_scan_sharded": [_PP, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "cmh_rank_map": [_PP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
+    "cmh_ap_reduce": [_PP, _vp, _i32, _vp, _vp],
     "cmh_map_finish": [_PP, _vp, _i32, _vp, _vp, _vp, _vp],
     "cmh_rank_topk": [_PP, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp],
     "cmh_fill_keys": [_vp, _i64, ctypes.c_uint64, _vp],
@@ -120,7 +122,7 @@ PROTOTYPES = {
     "cmh_head_mith_workspace_bytes": [_vp, _i64, _i32],
     "cmh_head_mith": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp],
 }
-_RESTYPES = {"cmh_last_error": ctypes.c_char_p, "cmh_encoder_workspace_bytes": ctypes.c_int64,
+_RESTYPES = {"cmh_last_error": ctypes.c_char_p, "cmh_launch_count": ctypes.c_ulonglong, "cmh_encoder_workspace_bytes": ctypes.c_int64,
              "cmh_head_mith_workspace_bytes": ctypes.c_int64}
 
 _lib: Optional[ctypes.CDLL] = None

@@ -76,9 +76,18 @@ def _back(out: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
     return out if like.is_cuda else out.cpu()
 
 
+def _needs_grad(*ts) -> bool:
+    """The similarity helpers are also called inside training losses (models/DCMHT/DCMHT.py:78, models/baseline/model.py:128)
+    on hash outputs that require grad.  The kernels are forward-only, so such calls keep the reference's own differentiable
+    torch expression (on the inputs' device) instead of silently cutting the graph."""
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
+
 # a4 -------------------------------------------------------------------------------------------------------
 def calc_label_sim(a: torch.Tensor, b: torch.Tensor):
     """``(a.matmul(b.T) > 0).float()`` (common/calc_utils.py:8-10); result on ``a``'s device."""
+    if _needs_grad(a, b):
+        return (a.matmul(b.transpose(0, 1)) > 0).float()
     return _back(_sim("label", a, b), a)
 
 
@@ -104,6 +113,8 @@ def generate_weight_sim(a: torch.Tensor, b: torch.Tensor):
 def euclidean_similarity(a: ArrayLike, b: ArrayLike):
     """Pairwise L2 distance (common/calc_utils.py:28-36): torch in -> torch out, numpy in -> numpy out."""
     if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor):
+        if _needs_grad(a, b):
+            return torch.cdist(a, b, p=2.0)
         return _back(_sim("euclid", a, b), a)
     elif isinstance(a, np.ndarray) and isinstance(b, np.ndarray):
         out = _sim("euclid", torch.from_numpy(np.ascontiguousarray(a)), torch.from_numpy(np.ascontiguousarray(b)))
@@ -116,6 +127,8 @@ def euclidean_similarity(a: ArrayLike, b: ArrayLike):
 def cosine_similarity(a: ArrayLike, b: ArrayLike):
     """Row-normalised gram (common/calc_utils.py:38-49); no epsilon: a zero row gives nan like the reference."""
     if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor):
+        if _needs_grad(a, b):
+            return torch.matmul(a / a.norm(dim=-1, keepdim=True), (b / b.norm(dim=-1, keepdim=True)).t())
         return _back(_sim("cosine", a, b), a)
     elif isinstance(a, np.ndarray) and isinstance(b, np.ndarray):
         out = _sim("cosine", torch.from_numpy(np.ascontiguousarray(a)), torch.from_numpy(np.ascontiguousarray(b)))
@@ -145,6 +158,39 @@ def calc_hammingDist(B1: torch.Tensor, B2: torch.Tensor) -> torch.Tensor:
 
 
 # a2 -------------------------------------------------------------------------------------------------------
+class _PackedCache:
+    """Packed labels of the last few distinct label tensors.  ``BaseTrainer.valid`` (runners/base.py:317-321) calls
+    calc_map_k four times with the same two label matrices (75 MB of int64 at C2): they are uploaded and packed once.
+    An entry is keyed by the tensor object (weak reference), its version counter, storage pointer, shape and device."""
+
+    def __init__(self, capacity: int = 4):
+        self.capacity = capacity
+        self.entries = []  # (weakref, version, data_ptr, shape, dtype, device, packed, bad_count)
+
+    def get(self, t: torch.Tensor, dev: torch.device):
+        import weakref
+
+        for e in self.entries:
+            if e[0]() is t and e[1] == t._version and e[2] == t.data_ptr() and e[3] == tuple(t.shape) and e[4] == t.dtype and e[5] == dev:
+                return e[6], e[7]
+        bad = R.new_bad_counter(dev)
+        packed = R.pack_labels(_to_dev(t.detach(), dev), bad)
+        nbad = int(bad.item())
+        try:
+            ref = weakref.ref(t)
+        except TypeError:
+            return packed, nbad
+        self.entries.insert(0, (ref, t._version, t.data_ptr(), tuple(t.shape), t.dtype, dev, packed, nbad))
+        del self.entries[self.capacity:]
+        return packed, nbad
+
+    def clear(self):
+        self.entries.clear()
+
+
+_LABEL_CACHE = _PackedCache()
+
+
 def _parity_reduce(tindex_rows: torch.Tensor, totals: torch.Tensor, running):
     """calc_utils.py:84-89 on the host for a slab of queries: same torch CPU ops, same order."""
     for row in range(tindex_rows.shape[0]):
@@ -155,13 +201,39 @@ def _parity_reduce(tindex_rows: torch.Tensor, totals: torch.Tensor, running):
     return running
 
 
+def _map_k_dense(qB, rB, query_L, retrieval_L, k, dev):
+    """calc_map_k for codes that are NOT +-1 (a 0 from ``sign_()`` of an exact zero, +-2 rows from the DistributedSampler
+    padding of runners/base.py:180-190,263-264): the reference still computes a value there (common/calc_utils.py:51-56,76),
+    so this path evaluates the same expression — fp32 ``0.5 * (K - q.r)`` (cmh_hamming_dense_f32), stable sort, AP loop —
+    on the GPU in query slabs.  Rare path: it materialises slab x N floats, which the packed evaluator never does."""
+    qf, rf = _as_f32_dev(qB, dev), _as_f32_dev(rB, dev)
+    ql, rl = _as_f32_dev(query_L, dev), _as_f32_dev(retrieval_L, dev)
+    Q, N = qf.shape[0], rf.shape[0]
+    slab = max(1, min(Q, (1 << 26) // max(N, 1)))
+    total_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    for lo in range(0, Q, slab):
+        hi = min(lo + slab, Q)
+        gnd = _sim("label", ql[lo:hi], rl)                      # [s, N] 0/1
+        hamm = R.hamming_dense(qf[lo:hi], rf)
+        order = torch.sort(hamm, dim=-1, stable=True)[1]
+        g = torch.gather(gnd, 1, order)
+        tsum = g.sum(dim=1)
+        total = torch.clamp(tsum, max=float(k))
+        crel = torch.cumsum(g, dim=1)                           # 1-based rank among the relevant items
+        pos = torch.arange(1, N + 1, device=dev, dtype=torch.float32)[None, :]
+        terms = torch.where((g > 0) & (crel <= total[:, None]), crel / pos, torch.zeros_like(crel))
+        total_sum += (terms.sum(dim=1, dtype=torch.float64) / total.to(torch.float64)).sum()   # 0/0 -> nan like the reference
+    return (total_sum / Q).to(torch.float32).cpu()
+
+
 def calc_map_k(qB, rB, query_L, retrieval_L, k=None, *, mode: Optional[str] = None):
     """mAP over the first ``min(R, k)`` relevant items of the full Hamming ranking
     (common/calc_utils.py:58-92).  Accepts tensors on any device; returns a 0-dim fp32 CPU tensor.
 
     Ties in distance are ranked by ascending gallery index (``torch.sort(..., stable=True)``), the
     canonical order of this repo; the reference's unstable CPU sort is unspecified there.
-    Raises ``ValueError`` if the codes are not +-1 or the labels not 0/1."""
+    Codes that are not exactly +-1 take the dense fp32 path (`_map_k_dense`) like the reference's own arithmetic;
+    labels are multi-hot: any non-zero entry counts as "has the class" (the reference tests ``gram > 0``)."""
     mode = mode or os.environ.get("CMH_MAP_MODE", "device")
     if mode not in ("device", "parity"):
         raise ValueError("mode must be 'device' or 'parity'")
@@ -169,22 +241,24 @@ def calc_map_k(qB, rB, query_L, retrieval_L, k=None, *, mode: Optional[str] = No
     dev = dev or _device()
     num_query = query_L.shape[0]
     nbits, ncls = rB.shape[1], retrieval_L.shape[1]
-    if nbits > 128 or ncls > 128:
-        raise CmhError("calc_map_k supports up to 128 bits and 128 classes (got %d, %d)" % (nbits, ncls))
     n = retrieval_L.shape[0]
     if k is None:
         k = n
+    if k <= 0:
+        raise ValueError("k must be positive or None")
     with torch.cuda.device(dev):
+        if nbits > 128 or ncls > 128:
+            return _map_k_dense(qB, rB, query_L, retrieval_L, k, dev)
         bad = R.new_bad_counter(dev)
         qp = R.pack_codes(_to_dev(qB.detach(), dev), bad)
         gp = R.pack_codes(_to_dev(rB.detach(), dev), bad)
-        qlp = R.pack_labels(_to_dev(query_L.detach(), dev), bad)
-        glp = R.pack_labels(_to_dev(retrieval_L.detach(), dev), bad)
+        qlp, _ = _LABEL_CACHE.get(query_L, dev)
+        glp, _ = _LABEL_CACHE.get(retrieval_L, dev)
         if mode == "device":
             res = R.map_k(qp, qlp, gp, glp, nbits, ncls, k)
             host = torch.stack([res.map, bad[0].to(torch.float64)]).cpu()
             if host[1] != 0:
-                raise ValueError("calc_map_k: codes must be +-1 and labels 0/1 (%d offending elements)" % int(host[1]))
+                return _map_k_dense(qB, rB, query_L, retrieval_L, k, dev)
             return host[0].to(torch.float32)
 
         # parity mode: integer ranks from the GPU, fp32 reduction by the reference's own CPU ops
@@ -194,7 +268,7 @@ def calc_map_k(qB, rB, query_L, retrieval_L, k=None, *, mode: Optional[str] = No
         sc = st.scan(plan, hist, 1, 0, k)
         totals = sc["total"][:num_query].cpu()
         if int(bad.item()) != 0:
-            raise ValueError("calc_map_k: codes must be +-1 and labels 0/1 (%d offending elements)" % int(bad.item()))
+            return _map_k_dense(qB, rB, query_L, retrieval_L, k, dev)
         cap = max(int(totals.max().item()), 1)
         rows = max(1, min(num_query, _PARITY_SLAB_BYTES // (4 * cap)))
         running = 0
@@ -218,31 +292,45 @@ def calc_map_k(qB, rB, query_L, retrieval_L, k=None, *, mode: Optional[str] = No
 def calc_map_k_packed(q_codes, r_codes, query_L, retrieval_L, nbits: int, k=None):
     """``calc_map_k`` on codes that are already bit-packed on the GPU (``models.get_code`` / ``encode_*_packed``:
     int32 ``[n, W]``, bit b of word w = code column 32w+b).  Labels as in the reference (multi-hot ``[n, C]``, any
-    device).  Returns the same 0-dim fp32 CPU tensor as ``calc_map_k`` — no +-1 fp32 buffers, no device->host hop of
-    the codes (the reference forces them to the CPU at common/calc_utils.py:62-64)."""
+    device; packed once and cached across calls).  Returns the same 0-dim fp32 CPU tensor as ``calc_map_k`` — no +-1
+    fp32 buffers, no device->host hop of the codes (the reference forces them to the CPU at common/calc_utils.py:62-64)."""
     dev = q_codes.device
     if not (q_codes.is_cuda and r_codes.is_cuda):
         raise CmhError("packed codes must live on the GPU")
     ncls = retrieval_L.shape[1]
     if nbits > 128 or ncls > 128:
-        raise CmhError("calc_map_k supports up to 128 bits and 128 classes (got %d, %d)" % (nbits, ncls))
+        raise CmhError("calc_map_k_packed supports up to 128 bits and 128 classes (got %d, %d)" % (nbits, ncls))
     if q_codes.shape[1] != R.code_words(nbits) or r_codes.shape[1] != R.code_words(nbits):
         raise CmhError("packed codes must have %d words per row for %d bits" % (R.code_words(nbits), nbits))
     k = retrieval_L.shape[0] if k is None else k
     with torch.cuda.device(dev):
-        bad = R.new_bad_counter(dev)
-        qlp = R.pack_labels(_to_dev(query_L.detach(), dev), bad)
-        glp = R.pack_labels(_to_dev(retrieval_L.detach(), dev), bad)
+        qlp, _ = _LABEL_CACHE.get(query_L, dev)
+        glp, _ = _LABEL_CACHE.get(retrieval_L, dev)
         res = R.map_k(q_codes.contiguous(), qlp, r_codes.contiguous(), glp, nbits, ncls, k)
-        host = torch.stack([res.map, bad[0].to(torch.float64)]).cpu()
-    if host[1] != 0:
-        raise ValueError("calc_map_k_packed: labels must be 0/1 (%d offending elements)" % int(host[1]))
-    return host[0].to(torch.float32)
+        return res.map.to(torch.float32).cpu()
 
 
-def hamming_topk(qB, rB, k: int):
+def valid_packed(query_img, query_txt, retrieval_img, retrieval_txt, query_labels, retrieval_labels, nbits: int, k=None):
+    """The four retrieval directions of ``BaseTrainer.valid`` / ``test`` (runners/base.py:317-321, 351-355) on packed codes
+    from ``models.get_code``: labels are uploaded and packed ONCE, the four evaluations are queued back to back and their
+    scalars come back in one device->host copy.  Returns ``(mAPi2t, mAPt2i, mAPi2i, mAPt2t)`` as 0-dim fp32 CPU tensors, in
+    the reference's order."""
+    dev = query_img.device
+    ncls = retrieval_labels.shape[1]
+    k = retrieval_labels.shape[0] if k is None else k
+    with torch.cuda.device(dev):
+        qlp, _ = _LABEL_CACHE.get(query_labels, dev)
+        glp, _ = _LABEL_CACHE.get(retrieval_labels, dev)
+        pairs = ((query_img, retrieval_txt), (query_txt, retrieval_img), (query_img, retrieval_img), (query_txt, retrieval_txt))
+        maps = [R.map_k(q.contiguous(), qlp, g.contiguous(), glp, nbits, ncls, k).map for q, g in pairs]
+        host = torch.stack(maps).to(torch.float32).cpu()
+    return tuple(host[i] for i in range(4))
+
+
+def hamming_topk(qB, rB, k: int, out=None):
     """First ``k`` columns of ``torch.sort(calc_hammingDist(qB, rB), stable=True)`` (calc_utils.py:76-77)
-    -> ``(dist [Q,k] fp32, index [Q,k] int64)`` on the inputs' device (north_star's "per-query top-k")."""
+    -> ``(dist [Q,k] fp32, index [Q,k] int64)`` on the inputs' device (north_star's "per-query top-k").
+    ``out=(dist, index)``: optional preallocated (e.g. pinned host) result tensors."""
     dev = qB.device if qB.is_cuda else (rB.device if rB.is_cuda else _device())
     nbits = rB.shape[1]
     with torch.cuda.device(dev):
@@ -250,19 +338,70 @@ def hamming_topk(qB, rB, k: int):
         qp = R.pack_codes(_to_dev(qB.detach(), dev), bad)
         gp = R.pack_codes(_to_dev(rB.detach(), dev), bad)
         keys = R.topk(qp, gp, nbits, k)
-        dist, idx = R.split_keys(keys)
-        if int(bad.item()) != 0:
-            raise ValueError("hamming_topk: codes must be +-1")
-    return _back(dist.to(torch.float32), qB), _back(idx, qB)
+        dist, idx = R.split_keys(keys, dist_dtype=torch.float32)
+        return _topk_result(dist, idx, bad, qB, out)
+
+
+def _topk_result(dist, idx, bad, like, out):
+    if out is not None:
+        out[0].copy_(dist, non_blocking=True)
+        out[1].copy_(idx, non_blocking=True)
+        nbad = int(bad.item())   # synchronises: the copies above have landed
+        res = out
+    else:
+        nbad = int(bad.item())
+        res = (_back(dist, like), _back(idx, like))
+    if nbad != 0:
+        raise ValueError("hamming_topk: codes must be +-1 (%d offending elements)" % nbad)
+    return res
+
+
+def hamming_topk_sharded(qB, rB_shard, k: int, idx_offset: int, n_geom: Optional[int] = None, group=None, evaluator=None,
+                         method: str = "auto", out=None, return_keys: bool = False):
+    """``hamming_topk`` with the gallery sharded by contiguous index range over the ranks of ``group`` (one process per GPU):
+    ``rB_shard`` holds this rank's items ``[idx_offset, idx_offset + len)``; queries are replicated.  Every rank returns the
+    same global ``(dist, index)``; ``out`` as in ``hamming_topk``.  ``return_keys=True`` skips the split / host copy and hands
+    back the int64 ``(dist << 32) | index`` keys on the GPU (ranks that do not need the result on the host)."""
+    dev = qB.device if qB.is_cuda else (rB_shard.device if rB_shard.is_cuda else _device())
+    nbits = rB_shard.shape[1]
+    with torch.cuda.device(dev):
+        ev = evaluator if evaluator is not None else R.ShardedEvaluator(group)
+        bad = R.new_bad_counter(dev)
+        qp = R.pack_codes(_to_dev(qB.detach(), dev), bad)
+        gp = R.pack_codes(_to_dev(rB_shard.detach(), dev), bad)
+        keys = ev.topk(qp, gp, nbits, k, idx_offset, n_geom=n_geom, method=method)
+        if return_keys:
+            if int(bad.item()) != 0:
+                raise ValueError("hamming_topk: codes must be +-1")
+            return keys
+        dist, idx = R.split_keys(keys, dist_dtype=torch.float32)
+        return _topk_result(dist, idx, bad, qB, out)
+
+
+_PATCHED = ("calc_label_sim", "generate_weight_sim", "euclidean_similarity", "cosine_similarity", "calc_hammingDist", "calc_map_k")
 
 
 def install_into_reference(module=None):
-    """Monkey-patch a loaded reference ``common.calc_utils`` module (or import it) with these functions."""
-    if module is None:
-        import importlib
+    """Bind this module's functions into a reference checkout.
 
+    The reference binds the evaluator by value at import time (``from common.calc_utils import calc_map_k`` in
+    runners/base.py:5, runners/MITH/runner.py:5, models/DCMHT/DCMHT.py:8, ...), so patching ``common.calc_utils`` alone is
+    not enough once those modules are loaded: every already-imported ``runners.*`` / ``models.*`` module whose attribute IS
+    the original reference function is re-bound too, and call sites imported later pick the patched module attributes.  Works
+    both before and after ``import runners``.  The similarity helpers stay differentiable: with an input that
+    requires grad they evaluate the reference's own torch expression (`_needs_grad`).  Returns the patched module."""
+    import importlib
+    import sys
+
+    if module is None:
         module = importlib.import_module("common.calc_utils")
-    for name in ("calc_label_sim", "generate_weight_sim", "euclidean_similarity", "cosine_similarity",
-                 "calc_hammingDist", "calc_map_k"):
+    originals = {name: getattr(module, name, None) for name in _PATCHED}
+    for name in _PATCHED:
         setattr(module, name, globals()[name])
+    for modname, mod in list(sys.modules.items()):
+        if mod is None or mod is module or not (modname.startswith("runners") or modname.startswith("models")):
+            continue
+        for name, orig in originals.items():
+            if orig is not None and getattr(mod, name, None) is orig:
+                setattr(mod, name, globals()[name])
     return module

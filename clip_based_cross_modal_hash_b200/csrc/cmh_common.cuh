@@ -12,6 +12,7 @@ namespace cmh {
 
 int fail(int code, const char* fmt, ...);  // records the per-thread message, returns `code`
 int sm_count_cached();                     // SM count of the current device (cached per device)
+void count_launch();                       // every kernel launch of this library (cmh_launch_count, bench.py's gpu_launches)
 
 #define CMH_CUDA_TRY(expr)                                                                        \
     do {                                                                                          \
@@ -23,6 +24,7 @@ int sm_count_cached();                     // SM count of the current device (ca
 
 #define CMH_LAUNCH_CHECK(name)                                                                    \
     do {                                                                                          \
+        ::cmh::count_launch();                                                                    \
         cudaError_t _e = cudaGetLastError();                                                      \
         if (_e != cudaSuccess)                                                                    \
             return ::cmh::fail(CMH_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
@@ -78,6 +80,7 @@ cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
         ++n;
     }
     cfg.attrs = attr, cfg.numAttrs = unsigned(n);
+    count_launch();
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -4,10 +4,15 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 namespace cmh {
 namespace {
 thread_local char g_err[1024] = "";
+std::atomic<unsigned long long> g_launches{0};
 }
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -49,6 +54,8 @@ extern "C" {
 int cmh_abi_version(void) { return CMH_ABI_VERSION; }
 
 const char* cmh_last_error(void) { return cmh::g_err; }
+
+unsigned long long cmh_launch_count(void) { return cmh::g_launches.load(std::memory_order_relaxed); }
 
 int cmh_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;

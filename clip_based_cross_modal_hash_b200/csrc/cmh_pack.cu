@@ -55,6 +55,128 @@ __global__ void __launch_bounds__(256) pack_kernel(const T* __restrict__ in, int
     if (bad_count && lane == 0 && bad) atomicAdd(bad_count, (unsigned long long)bad);
 }
 
+// Vector path (16-byte aligned rows, ncols a multiple of the 16-byte vector): a block stages whole rows.
+//   load   every thread issues 8 independent, fully coalesced 16-byte loads (a "slot" = one vector of V elements) before it
+//          touches any of them: 32 KB in flight per block, enough memory-level parallelism to stream at HBM speed;
+//   stage  the V sign / non-zero bits of a slot go to shared memory (one uint16 per slot);
+//   build  one thread per output word ORs the 32/V slots of its word together -> coalesced word stores.
+// Replaces the one-element-per-lane ballot loop for the bulk inputs (C4: 256 MB of +-1 fp32 gallery codes, C2: 75 MB of
+// int64 labels).
+template <class T>
+struct VecBits;  // bits of the V = 16/sizeof(T) elements of one 16-byte vector + number of "bad" elements
+template <>
+struct VecBits<float> {
+    static constexpr int V = 4;
+    template <bool IS_CODE>
+    static __device__ __forceinline__ void eval(const uint4& v, uint32_t& bits, unsigned& bad) {
+        const float f[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (IS_CODE) {
+                bits |= uint32_t(f[j] > 0.0f) << j;
+                bad += (f[j] != 1.0f && f[j] != -1.0f);
+            } else {
+                bits |= uint32_t(f[j] != 0.0f) << j;
+                bad += (f[j] != 0.0f && f[j] != 1.0f);
+            }
+        }
+    }
+};
+template <>
+struct VecBits<int32_t> {
+    static constexpr int V = 4;
+    template <bool IS_CODE>
+    static __device__ __forceinline__ void eval(const uint4& v, uint32_t& bits, unsigned& bad) {
+        const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bits |= uint32_t(e[j] != 0u) << j, bad += e[j] > 1u;
+    }
+};
+template <>
+struct VecBits<int64_t> {
+    static constexpr int V = 2;
+    template <bool IS_CODE>
+    static __device__ __forceinline__ void eval(const uint4& v, uint32_t& bits, unsigned& bad) {
+        bits |= uint32_t((v.x | v.y) != 0u) | (uint32_t((v.z | v.w) != 0u) << 1);
+        bad += (v.y != 0u || v.x > 1u) + (v.w != 0u || v.z > 1u);
+    }
+};
+template <>
+struct VecBits<uint8_t> {
+    static constexpr int V = 16;
+    template <bool IS_CODE>
+    static __device__ __forceinline__ void eval(const uint4& v, uint32_t& bits, unsigned& bad) {
+        const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t x = (e[j] >> (8 * b)) & 0xFFu;
+                bits |= uint32_t(x != 0u) << (4 * j + b);
+                bad += x > 1u;
+            }
+    }
+};
+
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_LOADS = 8;                          // 16-byte loads in flight per thread
+constexpr int PACK_SLOTS = PACK_THREADS * PACK_LOADS;  // slots staged per block iteration
+
+template <class T, bool IS_CODE>
+__global__ void __launch_bounds__(PACK_THREADS) pack_vec_kernel(const T* __restrict__ in, int64_t n, int ncols, int64_t ld,
+                                                                int words_dst, uint32_t* __restrict__ out,
+                                                                unsigned long long* __restrict__ bad_count) {
+    constexpr int V = VecBits<T>::V;
+    constexpr int SPW = 32 / V;  // slots per output word
+    __shared__ uint16_t nib[PACK_SLOTS];
+    const int tid = threadIdx.x;
+    const int spr = ncols / V;  // slots per row (ncols % V == 0, checked on the host)
+    const int rows_per_tile = PACK_SLOTS / spr;
+    const int words_src = (ncols + 31) / 32;
+    const int wshift = words_dst == 1 ? 0 : words_dst == 2 ? 1 : 2;
+    unsigned bad = 0;
+    for (int64_t row0 = int64_t(blockIdx.x) * rows_per_tile; row0 < n; row0 += int64_t(gridDim.x) * rows_per_tile) {
+        const int rows = n - row0 < rows_per_tile ? int(n - row0) : rows_per_tile;
+        const int nslots = rows * spr;
+        uint4 v[PACK_LOADS];
+#pragma unroll
+        for (int i = 0; i < PACK_LOADS; ++i) {
+            const int li = i * PACK_THREADS + tid;
+            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (li < nslots) {
+                const int r = li / spr, s = li - r * spr;
+                v[i] = __ldcs(reinterpret_cast<const uint4*>(in + (row0 + r) * ld + int64_t(s) * V));  // streamed once
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PACK_LOADS; ++i) {
+            const int li = i * PACK_THREADS + tid;
+            uint32_t bits = 0;
+            unsigned b = 0;
+            VecBits<T>::template eval<IS_CODE>(v[i], bits, b);
+            if (li < nslots) nib[li] = uint16_t(bits), bad += b;
+        }
+        __syncthreads();
+        const int nwords = rows << wshift;
+        for (int wi = tid; wi < nwords; wi += PACK_THREADS) {
+            const int r = wi >> wshift, w = wi & (words_dst - 1);
+            uint32_t word = 0;
+            if (w < words_src) {
+                const int first = w * SPW;
+                const int cnt = spr - first < SPW ? spr - first : SPW;
+                const uint16_t* src = nib + r * spr + first;
+#pragma unroll
+                for (int j = 0; j < SPW; ++j)
+                    if (j < cnt) word |= uint32_t(src[j]) << (j * V);
+            }
+            out[((row0 + r) << wshift) + w] = word;
+        }
+        __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xFFFFFFFFu, bad, o);
+    if (bad_count && (tid & 31) == 0 && bad) atomicAdd(bad_count, (unsigned long long)bad);
+}
+
 __global__ void __launch_bounds__(256) unpack_kernel(const uint32_t* __restrict__ packed, int64_t n, int nbits, int W,
                                                      float* __restrict__ out, int64_t ld) {
     const int64_t total = n * nbits;
@@ -69,6 +191,16 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint32_t* __restrict_
 template <class T, bool IS_CODE>
 int launch_pack(const T* in, int64_t n, int ncols, int64_t ld, int words_dst, uint32_t* out,
                 unsigned long long* bad, cudaStream_t st) {
+    constexpr int V = VecBits<T>::V;
+    if (ncols % V == 0 && ld % V == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && ncols / V <= PACK_SLOTS) {
+        const int rows_per_tile = PACK_SLOTS / (ncols / V);
+        int64_t blocks = ceil_div(n, rows_per_tile);
+        const int64_t cap = int64_t(sm_count_cached()) * 8;
+        if (blocks > cap) blocks = cap;
+        pack_vec_kernel<T, IS_CODE><<<unsigned(blocks), PACK_THREADS, 0, st>>>(in, n, ncols, ld, words_dst, out, bad);
+        CMH_LAUNCH_CHECK("pack_vec_kernel");
+        return CMH_OK;
+    }
     const int words_src = (ncols + 31) / 32;
     const int64_t total_words = n * words_dst;
     int64_t blocks = ceil_div(ceil_div(total_words, 32), 8);  // 8 warps per block, one 32-word group per warp pass

@@ -173,7 +173,7 @@ class CudaStages:
             "thresh": torch.empty(plan.Qpad, dtype=torch.int32, device=dev),
         }
         with torch.cuda.device(dev):
-            check(_lib.lib().cmh_scan(ctypes.byref(plan), hist_all.data_ptr(), world, rank, int(k) if k else 0,
+            check(_lib.lib().cmh_scan(ctypes.byref(plan), hist_all.data_ptr(), world, rank, 0 if k is None else int(k),
                                       o["within_all"].data_ptr(), _ptr(o["within_rel"]), o["below_all"].data_ptr(),
                                       _ptr(o["below_rel"]), o["tsum"].data_ptr(), o["total"].data_ptr(),
                                       o["thresh"].data_ptr(), _stream()))
@@ -203,7 +203,7 @@ class CudaStages:
         }
         with torch.cuda.device(dev):
             check(_lib.lib().cmh_scan_sharded(ctypes.byref(plan), hist_local.data_ptr(), totals_all.data_ptr(), world, rank,
-                                              int(k) if k else 0, o["within_all"].data_ptr(), o["within_rel"].data_ptr(),
+                                              0 if k is None else int(k), o["within_all"].data_ptr(), o["within_rel"].data_ptr(),
                                               o["below_all"].data_ptr(), o["below_rel"].data_ptr(), o["tsum"].data_ptr(),
                                               o["total"].data_ptr(), o["thresh"].data_ptr(), _stream()))
         return o
@@ -224,6 +224,15 @@ class CudaStages:
                                           sc["total"].data_ptr(), plan.N if n_total is None else n_total,
                                           ap_partial.data_ptr(), _ptr(tindex), cap, _stream()))
         return ap_partial
+
+    def ap_reduce(self, plan: Plan, ap_partial: torch.Tensor) -> torch.Tensor:
+        """[nchunks, Qpad] chunk partials -> [1, Qpad]: what a rank contributes to the AP exchange."""
+        dev = _need_cuda(ap_partial)
+        out = torch.empty((1, plan.Qpad), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_ap_reduce(ctypes.byref(plan), ap_partial.data_ptr(), ap_partial.numel() // plan.Qpad,
+                                           out.data_ptr(), _stream()))
+        return out
 
     def map_finish(self, plan: Plan, ap_partial_all: torch.Tensor, total: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         dev = _need_cuda(ap_partial_all, total)
@@ -255,14 +264,14 @@ class CudaStages:
         return out
 
 
-def split_keys(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """int64 keys -> (dist int32, index int64); empty slots -> -1."""
+def split_keys(keys: torch.Tensor, dist_dtype=torch.int32) -> Tuple[torch.Tensor, torch.Tensor]:
+    """int64 keys -> (dist int32 [or ``dist_dtype``], index int64); empty slots -> -1."""
     dev = _need_cuda(keys)
     dist = torch.empty(keys.shape, dtype=torch.int32, device=dev)
     idx = torch.empty(keys.shape, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         check(_lib.lib().cmh_split_keys(keys.data_ptr(), keys.numel(), dist.data_ptr(), idx.data_ptr(), _stream()))
-    return dist, idx
+    return (dist if dist_dtype == torch.int32 else dist.to(dist_dtype)), idx
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -277,55 +286,73 @@ class MapResult:
     tindex: Optional[torch.Tensor] = None  # [Q, cap] int32, 0 beyond total  (calc_utils.py:88)
 
 
-class Workspace:
-    """Grow-only device scratch for the one-shot C calls (the library allocates nothing)."""
-
-    def __init__(self):
-        self.buf: Optional[torch.Tensor] = None
-
-    def get(self, nbytes: int, device) -> torch.Tensor:
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
-            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        return self.buf
+TOPK_STAGE_NAMES = ("hist_kernel", "scan", "rank_topk_kernel")
+MAP_STAGE_NAMES = ("hist_kernel", "scan", "rank_map_kernel", "map_finish")
 
 
-_WS = Workspace()
+def _mark(stages) -> None:
+    """Append a CUDA event recorded on the current stream (bench.py's per-stage timing); no-op when stages is None."""
+    if stages is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        stages.append(e)
+
+
+def _check_k(k: Optional[int]) -> Optional[int]:
+    """k=None means the full ranking (calc_utils.py:70-71); anything else must be a positive count."""
+    if k is None:
+        return None
+    k = int(k)
+    if k <= 0:
+        raise CmhError("k must be a positive integer or None (got %d)" % k)
+    return k
 
 
 def map_k(qp, qlp, gp, glp, nbits: int, ncls: int, k: Optional[int] = None, want_tindex: bool = False,
-          tindex_cap: Optional[int] = None, target_blocks: int = 0) -> MapResult:
-    """calc_map_k on packed inputs, one GPU, via the one-shot C call ``cmh_map_k``."""
+          tindex_cap: Optional[int] = None, target_blocks: int = 0, stages: Optional[list] = None) -> MapResult:
+    """calc_map_k on packed inputs, one GPU: hist -> scan -> rank/AP -> mean (MAP_STAGE_NAMES).  Scratch comes from torch's
+    stream-aware caching allocator, so evaluations on different streams do not share buffers."""
     dev = _need_cuda(qp, qlp, gp, glp)
+    k = _check_k(k)
     Q, N = qp.shape[0], gp.shape[0]
-    plan = _lib.make_plan(Q, N, nbits, ncls, None, target_blocks)
-    ws = _WS.get(plan.workspace_bytes, dev)
-    out = torch.empty((), dtype=torch.float64, device=dev)
-    ap = torch.empty(Q, dtype=torch.float64, device=dev)
-    tsum = torch.empty(Q, dtype=torch.int32, device=dev)
-    total = torch.empty(Q, dtype=torch.int32, device=dev)
+    st = CudaStages()
+    plan = st.make_plan(Q, N, nbits, ncls, None, target_blocks)
     tindex = None
-    cap = 0
     if want_tindex:
         cap = int(tindex_cap if tindex_cap is not None else (min(k, N) if k else N))
-        cap = max(cap, 1)
-        tindex = torch.zeros((Q, cap), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        check(_lib.lib().cmh_map_k(ctypes.byref(plan), qp.data_ptr(), qlp.data_ptr(), gp.data_ptr(), glp.data_ptr(),
-                                   int(k) if k else 0, ws.data_ptr(), ws.numel(), out.data_ptr(), ap.data_ptr(),
-                                   tsum.data_ptr(), total.data_ptr(), _ptr(tindex), cap, _stream()))
-    return MapResult(out, ap, tsum, total, tindex)
+        tindex = torch.zeros((Q, max(cap, 1)), dtype=torch.int32, device=dev)
+    hist = st.hist(plan, qp, qlp, gp, glp)
+    _mark(stages)
+    sc = st.scan(plan, hist, 1, 0, k)
+    _mark(stages)
+    ap_partial = st.rank_map(plan, qp, qlp, gp, glp, sc, tindex)
+    _mark(stages)
+    ap, m = st.map_finish(plan, ap_partial, sc["total"])
+    _mark(stages)
+    return MapResult(m, ap, sc["tsum"][:Q], sc["total"][:Q], tindex)
 
 
-def topk(qp, gp, nbits: int, k: int, idx_offset: int = 0, target_blocks: int = 0) -> torch.Tensor:
-    """First k entries of the stable Hamming ranking as int64 keys ``(dist << 32) | index`` [Q, k]."""
-    dev = _need_cuda(qp, gp)
+def topk(qp, gp, nbits: int, k: int, idx_offset: int = 0, target_blocks: int = 0, stages: Optional[list] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """First k entries of the stable Hamming ranking as int64 keys ``(dist << 32) | index`` [Q, k] (TOPK_STAGE_NAMES)."""
+    dev = _need_cuda(qp, gp, out)
+    k = _check_k(k)
+    if k is None:
+        raise CmhError("top-k needs k")
     Q, N = qp.shape[0], gp.shape[0]
-    plan = _lib.make_plan(Q, N, nbits, 0, None, target_blocks)
-    ws = _WS.get(plan.workspace_bytes, dev)
-    keys = torch.empty((Q, k), dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
-        check(_lib.lib().cmh_topk(ctypes.byref(plan), qp.data_ptr(), gp.data_ptr(), k, idx_offset, ws.data_ptr(),
-                                  ws.numel(), keys.data_ptr(), _stream()))
+    st = CudaStages()
+    plan = st.make_plan(Q, N, nbits, 0, None, target_blocks)
+    keys = out if out is not None else torch.empty((Q, k), dtype=torch.int64, device=dev)
+    if keys.shape != (Q, k) or keys.dtype != torch.int64 or not keys.is_contiguous():
+        raise CmhError("out must be a contiguous int64 [Q, k] tensor")
+    if k > N:
+        keys.fill_(EMPTY_KEY)
+    hist = st.hist(plan, qp, None, gp, None)
+    _mark(stages)
+    sc = st.scan(plan, hist, 1, 0, k, with_rel=False)
+    _mark(stages)
+    st.rank_topk(plan, qp, gp, sc, k, idx_offset, keys=keys)
+    _mark(stages)
     return keys
 
 
@@ -385,14 +412,14 @@ class ShardedEvaluator:
         if tindex_cap:
             tindex = torch.zeros((Q, tindex_cap), dtype=torch.int32, device=qp.device)
         ap_partial = st.rank_map(plan, qp, qlp, gp_local, glp_local, sc, tindex, n_total=n_geom * self.world)
-        ap_all = self._gather(ap_partial)                      # [world, nchunks, Qpad]
+        ap_all = self._gather(st.ap_reduce(plan, ap_partial))  # [world, 1, Qpad]: one fp64 per query and rank
         ap, m = st.map_finish(plan, ap_all, sc["total"])
         if tindex is not None:                                 # each slot is written by exactly one rank
             self.dist.all_reduce(tindex, op=self.dist.ReduceOp.SUM, group=self.group)
         return MapResult(m, ap, sc["tsum"][:Q], sc["total"][:Q], tindex)
 
     def topk(self, qp, gp_local, nbits: int, k: int, idx_offset: int, n_geom: Optional[int] = None,
-             method: str = "rank_scatter") -> torch.Tensor:
+             method: str = "auto") -> torch.Tensor:
         """Global top-k keys [Q, k] (identical on every rank) of a gallery sharded by contiguous index range.
 
         ``rank_scatter`` (default): the counting formulation gives every item its GLOBAL stable rank from this rank's own
@@ -403,6 +430,9 @@ class ShardedEvaluator:
         (8 x 80 MB at C4), merge kernel.  Both are exact and give the same keys (tests/test_sharded_gloo.py, check_multi_gpu.py).
         """
         st = self.stages
+        k = _check_k(k)
+        if method == "auto":
+            method = "rank_scatter"
         Q, n_local = qp.shape[0], gp_local.shape[0]
         n_geom = self._geometry(n_local, n_geom, qp.device)
         plan = st.make_plan(Q, n_local, nbits, 0, n_geom)

@@ -50,6 +50,9 @@ extern "C" {
 
 int cmh_abi_version(void);
 const char* cmh_last_error(void);
+/* Kernels this library has launched in this process so far (every stream, every thread): what bench.py reports as
+ * gpu_launches.  Host-side counter, no device synchronisation. */
+unsigned long long cmh_launch_count(void);
 /* SM count / compute capability of the current device (synchronous). */
 int cmh_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -142,6 +145,10 @@ int cmh_rank_map(const cmh_plan* plan, const uint32_t* qcodes, const uint32_t* q
                  const uint32_t* within_rel, const uint32_t* below_all, const uint32_t* below_rel,
                  const int32_t* total, int64_t n_total, double* ap_partial, int32_t* tindex, int64_t cap,
                  void* stream);
+
+/* Sharded runs: a rank folds its chunk partials into ONE fp64 per query before the exchange (41 KB per rank at C2 instead of
+ * 2.4 MB): out[q] = sum_c ap_partial[c][q], chunk order, out = [Qpad]. */
+int cmh_ap_reduce(const cmh_plan* plan, const double* ap_partial, int nparts, double* out, void* stream);
 
 /* ap[q] = (sum over `nparts` chunk partials [nparts][Qpad], in index order) / total[q];
  * *map_out = (sum_q ap[q]) / Q in fp64, fixed order (calc_utils.py:89-90).  nan if any total is 0,

@@ -131,6 +131,13 @@ class OracleStages:
                     tindex[q, torch.from_numpy(r[sel])] = torch.from_numpy((ar[sel] + 1).astype(np.int32))
         return torch.from_numpy(ap)
 
+    def ap_reduce(self, plan, ap_partial):
+        parts = ap_partial.reshape(-1, plan.Qpad).numpy()
+        out = np.zeros(plan.Qpad, dtype=np.float64)
+        for p in parts:                                                           # chunk order, like ap_reduce_kernel
+            out = out + p
+        return torch.from_numpy(out[None, :].copy())
+
     def map_finish(self, plan, ap_partial_all, total):
         parts = ap_partial_all.reshape(-1, plan.Qpad).numpy()
         with np.errstate(invalid="ignore", divide="ignore"):

@@ -241,15 +241,20 @@ def test_query_without_relevant_items_gives_nan_like_reference():
     assert torch.isnan(cu.calc_map_k(qB, rB, qL, rL, 10, mode="parity"))
 
 
-def test_non_binary_inputs_raise():
+def test_non_binary_codes_do_not_raise_in_calc_map_k_but_do_in_topk():
+    """calc_map_k is a drop-in: the reference computes a value for codes containing 0 (common/calc_utils.py:51-56), so does the
+    shim (dense path, both modes).  hamming_topk has no reference counterpart for such codes and rejects them."""
     qB, rB = synth.random_codes(4, 32, 1), synth.random_codes(100, 32, 2)
     qL, rL = synth.random_labels(4, 10, 3), synth.random_labels(100, 10, 4)
     bad = rB.clone()
     bad[7, 7] = 0.0
+    want = float(port.calc_map_k(qB, bad, qL, rL, 10, stable=True))
+    assert abs(float(cu.calc_map_k(qB, bad, qL, rL, 10)) - want) <= 4e-7
+    assert abs(float(cu.calc_map_k(qB, bad, qL, rL, 10, mode="parity")) - want) <= 4e-7
     with pytest.raises(ValueError):
-        cu.calc_map_k(qB, bad, qL, rL, 10)
+        cu.hamming_topk(qB, bad, 10)
     with pytest.raises(ValueError):
-        cu.calc_map_k(qB, bad, qL, rL, 10, mode="parity")
+        cu.calc_map_k(qB, rB, qL, rL, 0)
 
 
 def test_similarity_helpers_match_reference():
@@ -321,3 +326,76 @@ def test_full_size_topk_properties():
     # nothing outside the list beats the list's last entry: check 16 queries with the C oracle
     od, oi = c_oracle.topk(_u32(qp)[:16, :2], _u32(gp)[:, :2], K, k)
     assert np.array_equal(dist[:16].cpu().numpy(), od) and np.array_equal(idx[:16].cpu().numpy(), oi)
+
+
+@pytest.mark.parametrize("K", [16, 32, 64, 128])
+def test_c4_full_size_topk_every_bit_width(K):
+    """BASELINE.json configs[3] at its FULL size (10 000 x 1 000 000, top-1000) for every code length of the sweep:
+    sortedness / uniqueness of all 10 000 result lists, and bit-exact (distance, index) lists for 16 queries against the C oracle."""
+    s = synth.CONFIGS["C4-%d" % K]
+    Q, N, k = s["Q"], s["N"], s["k"]
+    qB, rB = synth.random_codes(Q, K, 41 + K), synth.random_codes(N, K, 42 + K)
+    qp, gp = R.pack_codes(qB.to(DEV)), R.pack_codes(rB.to(DEV))
+    del qB, rB
+    keys = R.topk(qp, gp, K, k)
+    assert (keys[:, 1:] > keys[:, :-1]).all()
+    dist, idx = R.split_keys(keys)
+    assert int(idx.min()) >= 0 and int(idx.max()) < N and int(dist.min()) >= 0 and int(dist.max()) <= K
+    W = (K + 31) // 32
+    sub = np.arange(0, Q, Q // 16)[:16]
+    od, oi = c_oracle.topk(_u32(qp)[sub][:, :W], _u32(gp)[:, :W], K, k)
+    assert np.array_equal(dist.cpu().numpy()[sub], od) and np.array_equal(idx.cpu().numpy()[sub], oi)
+
+
+@pytest.mark.parametrize("kind", ["clustered", "all_equal", "two_values"])
+def test_topk_degenerate_distance_distributions(kind):
+    """Trained hash heads give clustered codes (huge tie buckets at tiny distances); the extreme is a gallery of identical codes.
+    The top-k must still be the first k of the stable (distance, index) order."""
+    Q, N, K, k = 300, 200_000, 64, 1000
+    if kind == "clustered":
+        qB, rB = synth.clustered_codes(Q, K, 5), synth.clustered_codes(N, K, 6)
+    elif kind == "all_equal":
+        qB = synth.random_codes(Q, K, 7)
+        rB = synth.random_codes(1, K, 8).expand(N, K).contiguous()
+    else:
+        qB = synth.random_codes(Q, K, 9)
+        two = synth.random_codes(2, K, 10)
+        rB = two[(torch.arange(N) % 7 == 0).long()].contiguous()
+    qp, gp = R.pack_codes(qB.to(DEV)), R.pack_codes(rB.to(DEV))
+    keys = R.topk(qp, gp, K, k)
+    dist, idx = R.split_keys(keys)
+    od, oi = c_oracle.topk(_u32(qp)[:, :2], _u32(gp)[:, :2], K, k)
+    assert np.array_equal(dist.cpu().numpy(), od) and np.array_equal(idx.cpu().numpy(), oi)
+
+
+def test_calc_map_k_non_binary_codes_take_the_dense_path():
+    """Codes with a 0 (sign_() of an exact zero) or +-2 rows (DistributedSampler padding + all_reduce SUM, runners/base.py:180-190,
+    263-264): the reference computes a value there, and so does the drop-in (dense fp32 path) — compared with the port."""
+    from oracle import calc_utils_port as port
+
+    Q, N, K, C = 40, 900, 32, 12
+    qB, rB = synth.random_codes(Q, K, 51), synth.random_codes(N, K, 52)
+    qL, rL = synth.random_labels(Q, C, 53), synth.random_labels(N, C, 54)
+    rB[5] *= 2.0
+    rB[17, 3] = 0.0
+    qB[2, 0] = 0.0
+    want = port.calc_map_k(qB, rB, qL, rL, 50, stable=True)
+    got = cu.calc_map_k(qB, rB, qL, rL, 50)
+    assert got.dtype == torch.float32 and got.device.type == "cpu" and got.dim() == 0
+    assert abs(float(got) - float(want)) <= 4e-7 * max(1.0, abs(float(want)))
+    # labels given as counts (non 0/1): the reference only tests gram > 0
+    qL2 = qL * 3
+    assert abs(float(cu.calc_map_k(qB.sign() + (qB == 0), rB.sign() + (rB == 0), qL2, rL, 50)) -
+               float(port.calc_map_k(qB.sign() + (qB == 0), rB.sign() + (rB == 0), qL2, rL, 50))) <= 4e-7
+
+
+def test_valid_packed_matches_four_calc_map_k_calls():
+    Q, N, K, C = 64, 3000, 64, 20
+    codes = [synth.random_codes(n, K, 60 + i) for i, n in enumerate((Q, Q, N, N))]
+    qL, rL = synth.random_labels(Q, C, 70), synth.random_labels(N, C, 71)
+    packed = [R.pack_codes(c.to(DEV)) for c in codes]
+    got = cu.valid_packed(packed[0], packed[1], packed[2], packed[3], qL, rL, K, None)
+    want = (cu.calc_map_k(codes[0], codes[3], qL, rL), cu.calc_map_k(codes[1], codes[2], qL, rL),
+            cu.calc_map_k(codes[0], codes[2], qL, rL), cu.calc_map_k(codes[1], codes[3], qL, rL))
+    for g, w in zip(got, want):
+        assert g.dtype == torch.float32 and g.device.type == "cpu" and float(g) == float(w)
