@@ -71,8 +71,16 @@ class Plan(ctypes.Structure):
     ]
 
 
+class TcOperands(ctypes.Structure):
+    """Mirror of ``struct cmh_tc_operands`` (include/cmh.h): int8 operand rows of the tensor-core ranking passes."""
+
+    _fields_ = [("q_codes", ctypes.c_void_p), ("q_labels", ctypes.c_void_p), ("g_codes", ctypes.c_void_p),
+                ("g_labels", ctypes.c_void_p), ("code_bytes", ctypes.c_int32), ("label_bytes", ctypes.c_int32)]
+
+
 _i32, _i64, _vp, _sz = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t
 _PP = ctypes.POINTER(Plan)
+_OP = ctypes.POINTER(TcOperands)
 
 # name -> argtypes (restype is int unless noted); kept in one table so tests can check every symbol of cmh.h
 PROTOTYPES = {
@@ -101,6 +109,11 @@ PROTOTYPES = {
     "cmh_split_keys": [_vp, _i64, _vp, _vp, _vp],
     "cmh_map_k": [_PP, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "cmh_topk": [_PP, _vp, _vp, _i64, _i64, _vp, _sz, _vp, _vp],
+    "cmh_tc_operand_bytes": [_i32],
+    "cmh_tc_expand": [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp],
+    "cmh_tc_hist": [_PP, _OP, _i32, _vp, _vp],
+    "cmh_tc_rank_topk": [_PP, _OP, _vp, _vp, _vp, _i64, _i64, _vp, _vp],
+    "cmh_tc_rank_map": [_PP, _OP, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
     "cmh_label_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],
     "cmh_cosine_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],
     "cmh_euclid_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],

@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import CmhError, Plan, check
+from ._lib import CmhError, Plan, TcOperands, check
 
 EMPTY_KEY = -1  # 0xFFFF_FFFF_FFFF_FFFF viewed as int64
 _LABEL_DT = {torch.int64: 0, torch.float32: 1, torch.uint8: 2, torch.bool: 2, torch.int32: 3}
@@ -144,19 +144,62 @@ def hamming_dense(b1: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------------
 # evaluator stages (one C entry point each)
 # ---------------------------------------------------------------------------------------------------------
+class Operands:
+    """int8 operand rows of the tensor-core ranking passes (``cmh_tc_*``), expanded once per evaluation from the packed words and
+    shared by the histogram and the rank pass.  Holds the device buffers alive."""
+
+    def __init__(self, q_codes, q_labels, g_codes, g_labels):
+        self.q_codes, self.q_labels, self.g_codes, self.g_labels = q_codes, q_labels, g_codes, g_labels
+        self.c = TcOperands(q_codes.data_ptr(), _ptr(q_labels), g_codes.data_ptr() if g_codes.numel() else None, 
+                            _ptr(g_labels) if (g_labels is not None and g_labels.numel()) else None,
+                            q_codes.shape[1], 0 if q_labels is None else q_labels.shape[1])
+
+
+def _expand(packed: torch.Tensor, rows: int, ncols: int, kind: int) -> torch.Tensor:
+    nb = _lib.lib().cmh_tc_operand_bytes(ncols)
+    if nb < 0:
+        raise CmhError("operand width %d not supported" % ncols)
+    out = torch.empty((rows, nb), dtype=torch.int8, device=packed.device)
+    check(_lib.lib().cmh_tc_expand(packed.data_ptr(), packed.shape[0], rows, packed.shape[1], ncols, kind, out.data_ptr(), _stream()))
+    return out
+
+
 class CudaStages:
     """The product's stage kernels.  ``ShardedEvaluator`` takes any object with these methods so that the
-    exchange logic can be exercised on CPU (gloo) in tests with an oracle-backed stand-in."""
+    exchange logic can be exercised on CPU (gloo) in tests with an oracle-backed stand-in.
+
+    ``tensor_cores=True`` (default): hist / rank_topk / rank_map run with the distances on tcgen05 (csrc/cmh_tc.cu) when the caller
+    passes the ``ops`` made by ``operands``; ``False`` keeps the XOR+POPC kernels of csrc/cmh_retrieval.cu (same results)."""
+
+    def __init__(self, tensor_cores: Optional[bool] = None):
+        if tensor_cores is None:
+            import os
+            tensor_cores = os.environ.get("CMH_NO_TC", "0") in ("", "0")
+        self.tensor_cores = bool(tensor_cores)
 
     def make_plan(self, Q, N, nbits, ncls, N_geom=None, target_blocks=0) -> Plan:
         return _lib.make_plan(Q, N, nbits, ncls, N_geom, target_blocks)
 
-    def hist(self, plan: Plan, qp, qlp, gp, glp) -> torch.Tensor:
+    def operands(self, plan: Plan, qp, qlp, gp, glp) -> Optional[Operands]:
+        """Expand the packed words into the int8 operand rows of the tensor-core passes (None when they are switched off)."""
+        if not self.tensor_cores:
+            return None
+        dev = _need_cuda(qp, qlp, gp, glp)
+        with torch.cuda.device(dev):
+            with_labels = qlp is not None and glp is not None and plan.ncls > 0
+            return Operands(_expand(qp, plan.Qpad, plan.nbits, 0), _expand(qlp, plan.Qpad, plan.ncls, 1) if with_labels else None,
+                            _expand(gp, gp.shape[0], plan.nbits, 0), _expand(glp, glp.shape[0], plan.ncls, 2) if with_labels else None)
+
+    def hist(self, plan: Plan, qp, qlp, gp, glp, ops: Optional[Operands] = None) -> torch.Tensor:
         dev = _need_cuda(qp, qlp, gp, glp)
         hist = torch.empty((plan.nchunks, plan.bins, plan.Qpad), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            check(_lib.lib().cmh_hist(ctypes.byref(plan), qp.data_ptr(), _ptr(qlp), gp.data_ptr(), _ptr(glp),
-                                      hist.data_ptr(), _stream()))
+            if ops is not None:
+                with_labels = qlp is not None and glp is not None and ops.q_labels is not None
+                check(_lib.lib().cmh_tc_hist(ctypes.byref(plan), ctypes.byref(ops.c), int(with_labels), hist.data_ptr(), _stream()))
+            else:
+                check(_lib.lib().cmh_hist(ctypes.byref(plan), qp.data_ptr(), _ptr(qlp), gp.data_ptr(), _ptr(glp),
+                                          hist.data_ptr(), _stream()))
         return hist
 
     def scan(self, plan: Plan, hist_all: torch.Tensor, world: int, rank: int, k: Optional[int],
@@ -209,7 +252,7 @@ class CudaStages:
         return o
 
     def rank_map(self, plan: Plan, qp, qlp, gp, glp, sc: Dict[str, torch.Tensor],
-                 tindex: Optional[torch.Tensor] = None, n_total: Optional[int] = None) -> torch.Tensor:
+                 tindex: Optional[torch.Tensor] = None, n_total: Optional[int] = None, ops: Optional[Operands] = None) -> torch.Tensor:
         dev = _need_cuda(qp, qlp, gp, glp, tindex)
         ap_partial = torch.empty((plan.nchunks, plan.Qpad), dtype=torch.float64, device=dev)
         cap = 0
@@ -217,6 +260,13 @@ class CudaStages:
             if tindex.dtype != torch.int32 or tindex.dim() != 2 or tindex.shape[0] < plan.Q or not tindex.is_contiguous():
                 raise CmhError("tindex must be a contiguous int32 [Q, cap] tensor")
             cap = tindex.shape[1]
+        nt = plan.N if n_total is None else n_total
+        if ops is not None and nt < (1 << 24):
+            with torch.cuda.device(dev):
+                check(_lib.lib().cmh_tc_rank_map(ctypes.byref(plan), ctypes.byref(ops.c), sc["within_all"].data_ptr(),
+                                                 sc["within_rel"].data_ptr(), sc["below_all"].data_ptr(), sc["below_rel"].data_ptr(),
+                                                 sc["total"].data_ptr(), nt, ap_partial.data_ptr(), _ptr(tindex), cap, _stream()))
+            return ap_partial
         with torch.cuda.device(dev):
             check(_lib.lib().cmh_rank_map(ctypes.byref(plan), qp.data_ptr(), qlp.data_ptr(), gp.data_ptr(),
                                           glp.data_ptr(), sc["within_all"].data_ptr(), sc["within_rel"].data_ptr(),
@@ -245,10 +295,16 @@ class CudaStages:
         return ap, out
 
     def rank_topk(self, plan: Plan, qp, gp, sc: Dict[str, torch.Tensor], k: int, idx_offset: int,
-                  keys: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  keys: Optional[torch.Tensor] = None, ops: Optional[Operands] = None) -> torch.Tensor:
         dev = _need_cuda(qp, gp)
         if keys is None:
             keys = torch.full((plan.Q, k), EMPTY_KEY, dtype=torch.int64, device=dev)
+        if ops is not None:
+            with torch.cuda.device(dev):
+                check(_lib.lib().cmh_tc_rank_topk(ctypes.byref(plan), ctypes.byref(ops.c), sc["within_all"].data_ptr(),
+                                                  sc["below_all"].data_ptr(), sc["thresh"].data_ptr(), k, idx_offset,
+                                                  keys.data_ptr(), _stream()))
+            return keys
         with torch.cuda.device(dev):
             check(_lib.lib().cmh_rank_topk(ctypes.byref(plan), qp.data_ptr(), gp.data_ptr(),
                                            sc["within_all"].data_ptr(), sc["below_all"].data_ptr(),
@@ -286,8 +342,8 @@ class MapResult:
     tindex: Optional[torch.Tensor] = None  # [Q, cap] int32, 0 beyond total  (calc_utils.py:88)
 
 
-TOPK_STAGE_NAMES = ("hist_kernel", "scan", "rank_topk_kernel")
-MAP_STAGE_NAMES = ("hist_kernel", "scan", "rank_map_kernel", "map_finish")
+TOPK_STAGE_NAMES = ("expand", "hist_kernel", "scan", "rank_topk_kernel")
+MAP_STAGE_NAMES = ("expand", "hist_kernel", "scan", "rank_map_kernel", "map_finish")
 
 
 def _mark(stages) -> None:
@@ -309,23 +365,26 @@ def _check_k(k: Optional[int]) -> Optional[int]:
 
 
 def map_k(qp, qlp, gp, glp, nbits: int, ncls: int, k: Optional[int] = None, want_tindex: bool = False,
-          tindex_cap: Optional[int] = None, target_blocks: int = 0, stages: Optional[list] = None) -> MapResult:
+          tindex_cap: Optional[int] = None, target_blocks: int = 0, stages: Optional[list] = None,
+          tensor_cores: Optional[bool] = None) -> MapResult:
     """calc_map_k on packed inputs, one GPU: hist -> scan -> rank/AP -> mean (MAP_STAGE_NAMES).  Scratch comes from torch's
     stream-aware caching allocator, so evaluations on different streams do not share buffers."""
     dev = _need_cuda(qp, qlp, gp, glp)
     k = _check_k(k)
     Q, N = qp.shape[0], gp.shape[0]
-    st = CudaStages()
+    st = CudaStages(tensor_cores)
     plan = st.make_plan(Q, N, nbits, ncls, None, target_blocks)
     tindex = None
     if want_tindex:
         cap = int(tindex_cap if tindex_cap is not None else (min(k, N) if k else N))
         tindex = torch.zeros((Q, max(cap, 1)), dtype=torch.int32, device=dev)
-    hist = st.hist(plan, qp, qlp, gp, glp)
+    ops = st.operands(plan, qp, qlp, gp, glp)
+    _mark(stages)
+    hist = st.hist(plan, qp, qlp, gp, glp, ops=ops)
     _mark(stages)
     sc = st.scan(plan, hist, 1, 0, k)
     _mark(stages)
-    ap_partial = st.rank_map(plan, qp, qlp, gp, glp, sc, tindex)
+    ap_partial = st.rank_map(plan, qp, qlp, gp, glp, sc, tindex, ops=ops)
     _mark(stages)
     ap, m = st.map_finish(plan, ap_partial, sc["total"])
     _mark(stages)
@@ -333,25 +392,27 @@ def map_k(qp, qlp, gp, glp, nbits: int, ncls: int, k: Optional[int] = None, want
 
 
 def topk(qp, gp, nbits: int, k: int, idx_offset: int = 0, target_blocks: int = 0, stages: Optional[list] = None,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, tensor_cores: Optional[bool] = None) -> torch.Tensor:
     """First k entries of the stable Hamming ranking as int64 keys ``(dist << 32) | index`` [Q, k] (TOPK_STAGE_NAMES)."""
     dev = _need_cuda(qp, gp, out)
     k = _check_k(k)
     if k is None:
         raise CmhError("top-k needs k")
     Q, N = qp.shape[0], gp.shape[0]
-    st = CudaStages()
+    st = CudaStages(tensor_cores)
     plan = st.make_plan(Q, N, nbits, 0, None, target_blocks)
     keys = out if out is not None else torch.empty((Q, k), dtype=torch.int64, device=dev)
     if keys.shape != (Q, k) or keys.dtype != torch.int64 or not keys.is_contiguous():
         raise CmhError("out must be a contiguous int64 [Q, k] tensor")
     if k > N:
         keys.fill_(EMPTY_KEY)
-    hist = st.hist(plan, qp, None, gp, None)
+    ops = st.operands(plan, qp, None, gp, None)
+    _mark(stages)
+    hist = st.hist(plan, qp, None, gp, None, ops=ops)
     _mark(stages)
     sc = st.scan(plan, hist, 1, 0, k, with_rel=False)
     _mark(stages)
-    st.rank_topk(plan, qp, gp, sc, k, idx_offset, keys=keys)
+    st.rank_topk(plan, qp, gp, sc, k, idx_offset, keys=keys, ops=ops)
     _mark(stages)
     return keys
 
@@ -404,14 +465,16 @@ class ShardedEvaluator:
         Q, n_local = qp.shape[0], gp_local.shape[0]
         n_geom = self._geometry(n_local, n_geom, qp.device)
         plan = st.make_plan(Q, n_local, nbits, ncls, n_geom)
-        hist = st.hist(plan, qp, qlp, gp_local, glp_local)
+        ops = st.operands(plan, qp, qlp, gp_local, glp_local) if hasattr(st, "operands") else None
+        kw = {"ops": ops} if ops is not None else {}
+        hist = st.hist(plan, qp, qlp, gp_local, glp_local, **kw)
         # a rank's chunks follow all chunks of the lower ranks: only the per-bucket totals travel
         totals_all = self._gather(st.hist_totals(plan, hist))  # [world, 2, bins, Qpad]
         sc = st.scan_sharded(plan, hist, totals_all, self.world, self.rank, k)
         tindex = None
         if tindex_cap:
             tindex = torch.zeros((Q, tindex_cap), dtype=torch.int32, device=qp.device)
-        ap_partial = st.rank_map(plan, qp, qlp, gp_local, glp_local, sc, tindex, n_total=n_geom * self.world)
+        ap_partial = st.rank_map(plan, qp, qlp, gp_local, glp_local, sc, tindex, n_total=n_geom * self.world, **kw)
         ap_all = self._gather(st.ap_reduce(plan, ap_partial))  # [world, 1, Qpad]: one fp64 per query and rank
         ap, m = st.map_finish(plan, ap_all, sc["total"])
         if tindex is not None:                                 # each slot is written by exactly one rank
@@ -436,16 +499,18 @@ class ShardedEvaluator:
         Q, n_local = qp.shape[0], gp_local.shape[0]
         n_geom = self._geometry(n_local, n_geom, qp.device)
         plan = st.make_plan(Q, n_local, nbits, 0, n_geom)
-        hist = st.hist(plan, qp, None, gp_local, None)
+        ops = st.operands(plan, qp, None, gp_local, None) if hasattr(st, "operands") else None
+        kw = {"ops": ops} if ops is not None else {}
+        hist = st.hist(plan, qp, None, gp_local, None, **kw)
         if method == "allgather_merge":
             sc = st.scan(plan, hist, 1, 0, k, with_rel=False)      # local ranking of this shard
-            keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset)
+            keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset, **kw)
             parts = self._gather(keys)                             # [world, Q, k]
             return st.topk_merge(parts)
         if method != "rank_scatter":
             raise CmhError("unknown top-k exchange %r" % method)
         totals_all = self._gather(st.hist_totals(plan, hist))      # [world, 2, bins, Qpad]
         sc = st.scan_sharded(plan, hist, totals_all, self.world, self.rank, k)
-        keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset)  # slots of global rank < k owned by this shard
+        keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset, **kw)  # slots of global rank < k owned by this shard
         self.dist.all_reduce(keys, op=self.dist.ReduceOp.MAX, group=self.group)   # EMPTY = -1 < every real key
         return keys

@@ -165,6 +165,36 @@ int cmh_rank_topk(const cmh_plan* plan, const uint32_t* qcodes, const uint32_t* 
                   int64_t idx_offset, uint64_t* keys, void* stream);
 int cmh_fill_keys(uint64_t* keys, int64_t count, uint64_t value, void* stream);
 
+/* ---- T: the ranking passes on the tensor cores (tcgen05.mma.kind::i8) -------------------------------------------------
+ * +-1 codes make calc_hammingDist a dense contraction (it IS one in the reference: common/calc_utils.py:55); so is the label
+ * test query_L.mm(retrieval_L.T) > 0 (calc_utils.py:72).  The cmh_tc_* entry points compute both on the tensor pipe
+ * (int8 operands, int32 accumulators in tensor memory) and keep the counting formulation of cmh_hist / cmh_rank_topk /
+ * cmh_rank_map unchanged: same plan, same outputs bit for bit, the scan entry points above are shared.
+ * Operands are int8 rows expanded from the bit-packed words (caller-owned buffers, 16-byte aligned):
+ *   codes  [rows][code_bytes]   +1 / -1, zero beyond nbits; code_bytes  = cmh_tc_operand_bytes(nbits) in {32, 64, 128}
+ *   labels [rows][label_bytes]  -128 (query side) / +8 (gallery side) per class; label_bytes = cmh_tc_operand_bytes(ncls)
+ * Query operands have Qpad rows (rows >= Q are filled by cmh_tc_expand), gallery operands exactly N rows. */
+typedef struct cmh_tc_operands {
+    const int8_t* q_codes;
+    const int8_t* q_labels; /* NULL for top-k */
+    const int8_t* g_codes;
+    const int8_t* g_labels; /* NULL for top-k */
+    int32_t code_bytes, label_bytes;
+} cmh_tc_operands;
+int cmh_tc_operand_bytes(int n); /* 32, 64 or 128; <0 if n is outside 1..128 */
+/* packed [n][nwords] -> out [rows][cmh_tc_operand_bytes(ncols)]; kind 0 = codes (either side), 1 = query labels, 2 = gallery labels;
+ * rows >= n are padding (codes: the all -1 code, labels: zero). */
+int cmh_tc_expand(const uint32_t* packed, int64_t n, int64_t rows, int nwords, int ncols, int kind, int8_t* out, void* stream);
+/* == cmh_hist (with_labels = 0: relevance counts are 0) */
+int cmh_tc_hist(const cmh_plan* plan, const cmh_tc_operands* ops, int with_labels, uint32_t* hist, void* stream);
+/* == cmh_rank_topk */
+int cmh_tc_rank_topk(const cmh_plan* plan, const cmh_tc_operands* ops, const uint32_t* within_all, const uint32_t* below_all,
+                     const int32_t* thresh, int64_t k, int64_t idx_offset, uint64_t* keys, void* stream);
+/* == cmh_rank_map for n_total < 2^24 (fp32 running ranks) */
+int cmh_tc_rank_map(const cmh_plan* plan, const cmh_tc_operands* ops, const uint32_t* within_all, const uint32_t* within_rel,
+                    const uint32_t* below_all, const uint32_t* below_rel, const int32_t* total, int64_t n_total,
+                    double* ap_partial, int32_t* tindex, int64_t cap, void* stream);
+
 /* ---- R5: merge of per-shard partial top-k after ONE all-gather -----------------------------------------
  * parts = [world][Q][k] sorted keys (0xFFFF...F = empty slot); out[q] = the k smallest keys. */
 int cmh_topk_merge(const uint64_t* parts, int world, int64_t Q, int64_t k, uint64_t* out, void* stream);

@@ -1,0 +1,116 @@
+"""GPU: the tensor-core ranking passes (csrc/cmh_tc.cu, tcgen05.mma.kind::i8) against the XOR+POPC kernels of
+csrc/cmh_retrieval.cu and the numpy oracle — bit-exact integer stages for every operand width (32/64/128-byte swizzle rows),
+with and without the label block, on ragged shapes."""
+import numpy as np
+import pytest
+import torch
+
+from clip_based_cross_modal_hash_b200 import retrieval as R
+from clip_based_cross_modal_hash_b200 import synth
+from oracle import hamming_oracle as ho
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def _inputs(Q, N, K, C, seed):
+    qp = R.pack_codes(synth.random_codes(Q, K, seed).to(DEV))
+    gp = R.pack_codes(synth.random_codes(N, K, seed + 1).to(DEV))
+    if C == 0:
+        return qp, gp, None, None
+    qlp = R.pack_labels(synth.random_labels(Q, C, seed + 2, p=0.15).to(DEV))
+    glp = R.pack_labels(synth.random_labels(N, C, seed + 3, p=0.15).to(DEV))
+    return qp, gp, qlp, glp
+
+
+@pytest.mark.parametrize("K", [8, 16, 32, 33, 64, 100, 128])
+def test_expand_matches_numpy(K):
+    n, rows = 37, 128
+    codes = synth.random_codes(n, K, 3)
+    packed = R.pack_codes(codes.to(DEV))
+    out = R._expand(packed, rows, K, 0).cpu().numpy()
+    KP = out.shape[1]
+    assert KP == (32 if K <= 32 else 64 if K <= 64 else 128)
+    want = np.zeros((rows, KP), dtype=np.int8)
+    want[:n, :K] = codes.numpy().astype(np.int8)
+    want[n:, :K] = -1
+    assert np.array_equal(out, want)
+    for kind, val in ((1, -128), (2, 8)):
+        lab = synth.random_labels(n, K, 5)
+        lp = R.pack_labels(lab.to(DEV))
+        got = R._expand(lp, rows, K, kind).cpu().numpy()
+        w = np.zeros((rows, KP), dtype=np.int8)
+        w[:n, :K] = (lab.numpy() != 0) * val
+        assert np.array_equal(got, w)
+
+
+SHAPES = [(5, 70), (130, 1000), (128, 64), (257, 4097), (300, 70_001)]
+
+
+@pytest.mark.parametrize("K", [16, 32, 48, 64, 96, 128])
+@pytest.mark.parametrize("C", [0, 24, 40, 80])
+@pytest.mark.parametrize("Q,N", SHAPES)
+def test_tc_stages_equal_popc_stages(Q, N, K, C):
+    qp, gp, qlp, glp = _inputs(Q, N, K, C, 11 * K + C + Q)
+    tc, pc = R.CudaStages(True), R.CudaStages(False)
+    plan = tc.make_plan(Q, N, K, C, None, 64 if N < 5000 else 0)
+    ops = tc.operands(plan, qp, qlp, gp, glp)
+    h_tc = tc.hist(plan, qp, qlp, gp, glp, ops=ops)
+    h_pc = pc.hist(plan, qp, qlp, gp, glp)
+    assert torch.equal(h_tc[:, :, :Q], h_pc[:, :, :Q])
+    k = min(50, N)
+    sc = pc.scan(plan, h_pc, 1, 0, k, with_rel=C > 0)
+    keys_tc = tc.rank_topk(plan, qp, gp, sc, k, 7, ops=ops)
+    keys_pc = pc.rank_topk(plan, qp, gp, sc, k, 7)
+    assert torch.equal(keys_tc, keys_pc)
+    if C > 0:
+        sc = pc.scan(plan, h_pc, 1, 0, None)
+        cap = 64
+        t_tc = torch.zeros((Q, cap), dtype=torch.int32, device=DEV)
+        t_pc = torch.zeros((Q, cap), dtype=torch.int32, device=DEV)
+        ap_tc = tc.rank_map(plan, qp, qlp, gp, glp, sc, t_tc, ops=ops)
+        ap_pc = pc.rank_map(plan, qp, qlp, gp, glp, sc, t_pc)
+        assert torch.equal(t_tc, t_pc)
+        assert torch.equal(ap_tc[:, :Q], ap_pc[:, :Q])          # same fp32 quotients, same fp64 summation order
+        ap2 = tc.rank_map(plan, qp, qlp, gp, glp, sc, None, ops=ops)
+        assert torch.equal(ap2[:, :Q], ap_pc[:, :Q])
+
+
+@pytest.mark.parametrize("K,C", [(16, 24), (64, 80), (128, 21)])
+def test_tc_histogram_matches_numpy_oracle(K, C):
+    Q, N = 70, 3000
+    qp, gp, qlp, glp = _inputs(Q, N, K, C, 5)
+    st = R.CudaStages(True)
+    plan = st.make_plan(Q, N, K, C, None, 8)
+    ops = st.operands(plan, qp, qlp, gp, glp)
+    h = _u32(st.hist(plan, qp, qlp, gp, glp, ops=ops))
+    W = (K + 31) // 32
+    d = ho.hamming_matrix(_u32(qp)[:, :W], _u32(gp)[:, :W]).astype(np.int64)
+    rel = ((_u32(qlp)[:, None, :] & _u32(glp)[None, :, :]) != 0).any(axis=2)
+    for c in range(plan.nchunks):
+        lo, hi = c * plan.chunk_items, min((c + 1) * plan.chunk_items, N)
+        for q in range(0, Q, 7):
+            ha = np.bincount(d[q, lo:hi], minlength=plan.bins)
+            hr = np.bincount(d[q, lo:hi][rel[q, lo:hi]], minlength=plan.bins)
+            assert np.array_equal(h[c, :, q] & 0xFFFF, ha) and np.array_equal(h[c, :, q] >> 16, hr)
+
+
+def test_tc_many_shared_classes_do_not_leak_into_the_distance():
+    """every query shares ALL classes with every gallery item: the label term of the accumulator is at its maximum."""
+    Q, N, K, C = 64, 2000, 128, 128
+    qp = R.pack_codes(synth.random_codes(Q, K, 1).to(DEV))
+    gp = R.pack_codes(synth.random_codes(N, K, 2).to(DEV))
+    qlp = R.pack_labels(torch.ones(Q, C, dtype=torch.int64, device=DEV))
+    glp = R.pack_labels(torch.ones(N, C, dtype=torch.int64, device=DEV))
+    tc, pc = R.CudaStages(True), R.CudaStages(False)
+    plan = tc.make_plan(Q, N, K, C, None, 4)
+    ops = tc.operands(plan, qp, qlp, gp, glp)
+    assert torch.equal(tc.hist(plan, qp, qlp, gp, glp, ops=ops)[:, :, :Q], pc.hist(plan, qp, qlp, gp, glp)[:, :, :Q])
+
+
+def test_tc_is_the_default_path():
+    assert R.CudaStages().tensor_cores is True
