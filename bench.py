@@ -333,7 +333,7 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
         out["parity_check"] = chk
         del gp_full
     if world == 1 and want_stage and stage_ms is not None:
-        names = R.TOPK_STAGE_NAMES[:len(stage_ms) - 1]
+        names = R.TOPK_FAST_STAGE_NAMES if len(stage_ms) == 7 else R.TOPK_STAGE_NAMES
         out["stage_ms"] = {"pack": stage_ms[0] / steps, **{n: v / steps for n, v in zip(names, stage_ms[1:])}}
     n_local = hi - lo
     out["survey_8d"] = survey_roofline(Q, n_local, K, k, out["ms_per_step"], peaks, out["clocks"].get("sm_mhz"))

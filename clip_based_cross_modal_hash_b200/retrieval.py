@@ -311,6 +311,38 @@ class CudaStages:
                                            sc["thresh"].data_ptr(), k, idx_offset, keys.data_ptr(), _stream()))
         return keys
 
+    # ---- candidate path of the top-k (cmh_tc_topk_*) ----
+    def topk_cutoff(self, plan_s: Plan, hist_s: torch.Tensor, n_local: int, k: int) -> torch.Tensor:
+        cutoff = torch.empty(plan_s.Qpad, dtype=torch.int32, device=hist_s.device)
+        with torch.cuda.device(hist_s.device):
+            check(_lib.lib().cmh_tc_topk_cutoff(ctypes.byref(plan_s), hist_s.data_ptr(), n_local, k, cutoff.data_ptr(), _stream()))
+        return cutoff
+
+    def topk_collect(self, plan: Plan, ops: Operands, cutoff: torch.Tensor, cap: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        dev = cutoff.device
+        cand = torch.empty((plan.nchunks, plan.Qpad, cap), dtype=torch.int32, device=dev)
+        cnt = torch.empty((plan.nchunks, plan.Qpad), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_tc_topk_collect(ctypes.byref(plan), ctypes.byref(ops.c), cutoff.data_ptr(), cap, cand.data_ptr(),
+                                                 cnt.data_ptr(), _stream()))
+        return cand, cnt
+
+    def topk_count(self, plan: Plan, cap: int, cand: torch.Tensor, cnt: torch.Tensor, k: int) -> torch.Tensor:
+        """-> int32 [bins + 1, Qpad]: rows 0..bins-1 = this shard's candidates per distance, element [bins, 0] = "take the exact
+        path" flag (a list overflowed / a cutoff was too tight)."""
+        tot = torch.zeros((plan.bins + 1, plan.Qpad), dtype=torch.int32, device=cand.device)
+        with torch.cuda.device(cand.device):
+            check(_lib.lib().cmh_tc_topk_count(ctypes.byref(plan), cap, cand.data_ptr(), cnt.data_ptr(), k, tot.data_ptr(),
+                                               tot[plan.bins].data_ptr(), _stream()))
+        return tot
+
+    def topk_place(self, plan: Plan, cap: int, cand: torch.Tensor, cnt: torch.Tensor, totals_all: torch.Tensor, world: int,
+                   rank: int, k: int, idx_offset: int, keys: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(cand.device):
+            check(_lib.lib().cmh_tc_topk_place(ctypes.byref(plan), cap, cand.data_ptr(), cnt.data_ptr(), totals_all.data_ptr(),
+                                               (plan.bins + 1) * plan.Qpad, world, rank, k, idx_offset, keys.data_ptr(), _stream()))
+        return keys
+
     def topk_merge(self, parts: torch.Tensor) -> torch.Tensor:
         dev = _need_cuda(parts)
         world, Q, k = parts.shape
@@ -342,7 +374,47 @@ class MapResult:
     tindex: Optional[torch.Tensor] = None  # [Q, cap] int32, 0 beyond total  (calc_utils.py:88)
 
 
-TOPK_STAGE_NAMES = ("expand", "hist_kernel", "scan", "rank_topk_kernel")
+TOPK_STAGE_NAMES = ("expand", "hist_kernel", "scan", "rank_topk_kernel")                       # exact two-pass path
+TOPK_FAST_STAGE_NAMES = ("expand", "sample_hist+cutoff", "collect_kernel", "count", "place")  # candidate path
+CAND_MIN_ITEMS = 65536   # shards smaller than this take the two-pass path directly
+
+
+def candidate_sample(n_local: int) -> int:
+    """Size of the gallery prefix whose exact histogram sets the per-query cutoffs: 1/16 of the shard, 4096..65536 items."""
+    return max(4096, min(65536, (n_local // 16) // 512 * 512))
+
+
+def candidate_cap(plan: Plan, k: int) -> int:
+    """Capacity of one (chunk, query) candidate list: 8x the mean of a k-candidate query, power of two in [64, 1024]."""
+    want = max(64, 8 * k // max(plan.nchunks, 1))
+    cap = 64
+    while cap < want and cap < 1024:
+        cap *= 2
+    return cap
+
+
+def candidate_path_ok(st, plan: Plan, n_local: int, k: int) -> bool:
+    return (bool(getattr(st, "tensor_cores", False)) and hasattr(st, "topk_collect") and n_local >= CAND_MIN_ITEMS and 16 * k <= n_local
+            and (plan.nchunks + 1) * plan.bins * 4 <= 200 * 1024)   # cand_place_kernel keeps [nchunks][bins] counters per query
+
+
+def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None):
+    """sample histogram -> cutoff -> one tensor-core pass -> per-distance totals (+ fallback flag).  Returns (cap, cand, cnt, tot)."""
+    n_s = min(candidate_sample(plan.N), plan.N)
+    if n_s > 0:
+        plan_s = st.make_plan(plan.Q, n_s, plan.nbits, 0)
+        hist_s = st.hist(plan_s, qp, None, gp[:n_s], None, ops=ops)
+        cutoff = st.topk_cutoff(plan_s, hist_s, plan.N, k)
+    else:   # an empty shard has no candidates
+        cutoff = torch.full((plan.Qpad,), -1, dtype=torch.int32, device=qp.device)
+    _mark(stages)
+    cap = candidate_cap(plan, k)
+    cand, cnt = st.topk_collect(plan, ops, cutoff, cap)
+    _mark(stages)
+    tot = st.topk_count(plan, cap, cand, cnt, k)
+    _mark(stages)
+    return cap, cand, cnt, tot
+
 MAP_STAGE_NAMES = ("expand", "hist_kernel", "scan", "rank_map_kernel", "map_finish")
 
 
@@ -392,8 +464,13 @@ def map_k(qp, qlp, gp, glp, nbits: int, ncls: int, k: Optional[int] = None, want
 
 
 def topk(qp, gp, nbits: int, k: int, idx_offset: int = 0, target_blocks: int = 0, stages: Optional[list] = None,
-         out: Optional[torch.Tensor] = None, tensor_cores: Optional[bool] = None) -> torch.Tensor:
-    """First k entries of the stable Hamming ranking as int64 keys ``(dist << 32) | index`` [Q, k] (TOPK_STAGE_NAMES)."""
+         out: Optional[torch.Tensor] = None, tensor_cores: Optional[bool] = None, exact: Optional[bool] = None) -> torch.Tensor:
+    """First k entries of the stable Hamming ranking as int64 keys ``(dist << 32) | index`` [Q, k].
+
+    Large galleries take the candidate path (TOPK_FAST_STAGE_NAMES): per-query cutoff from the exact histogram of a gallery prefix,
+    one tensor-core pass that keeps only items within the cutoff, per-query placement — verified on the device (enough
+    candidates, no list overflow); if the check fails, or with ``exact=True``, the two-pass counting path (TOPK_STAGE_NAMES) runs.
+    Both give the same keys."""
     dev = _need_cuda(qp, gp, out)
     k = _check_k(k)
     if k is None:
@@ -408,6 +485,15 @@ def topk(qp, gp, nbits: int, k: int, idx_offset: int = 0, target_blocks: int = 0
         keys.fill_(EMPTY_KEY)
     ops = st.operands(plan, qp, None, gp, None)
     _mark(stages)
+    if exact is not True and candidate_path_ok(st, plan, N, k):
+        cap, cand, cnt, tot = collect_candidates(st, plan, ops, qp, gp, k, stages)
+        st.topk_place(plan, cap, cand, cnt, tot, 1, 0, k, idx_offset, keys)
+        _mark(stages)
+        if int(tot[plan.bins, 0].item()) == 0:     # verified: every cutoff was wide enough and no list overflowed
+            return keys
+        if stages is not None:
+            del stages[1:]                          # the exact path below re-times its own stages
+            _mark(stages)
     hist = st.hist(plan, qp, None, gp, None, ops=ops)
     _mark(stages)
     sc = st.scan(plan, hist, 1, 0, k, with_rel=False)
@@ -482,7 +568,7 @@ class ShardedEvaluator:
         return MapResult(m, ap, sc["tsum"][:Q], sc["total"][:Q], tindex)
 
     def topk(self, qp, gp_local, nbits: int, k: int, idx_offset: int, n_geom: Optional[int] = None,
-             method: str = "auto") -> torch.Tensor:
+             method: str = "auto", exact: Optional[bool] = None) -> torch.Tensor:
         """Global top-k keys [Q, k] (identical on every rank) of a gallery sharded by contiguous index range.
 
         ``rank_scatter`` (default): the counting formulation gives every item its GLOBAL stable rank from this rank's own
@@ -501,6 +587,16 @@ class ShardedEvaluator:
         plan = st.make_plan(Q, n_local, nbits, 0, n_geom)
         ops = st.operands(plan, qp, None, gp_local, None) if hasattr(st, "operands") else None
         kw = {"ops": ops} if ops is not None else {}
+        if (method != "allgather_merge" and exact is not True and ops is not None
+                and candidate_path_ok(st, plan, n_geom, k)):   # decided on the common geometry: same path on every rank
+            # candidate path: local cutoffs guarantee >= min(k, n_local) LOCAL candidates, hence every item of the global top-k
+            cap, cand, cnt, tot = collect_candidates(st, plan, ops, qp, gp_local, k)
+            tot_all = self._gather(tot)                            # [world, bins + 1, Qpad]: per-distance totals + fallback flag
+            keys = torch.full((Q, k), EMPTY_KEY, dtype=torch.int64, device=qp.device)
+            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys)
+            self._exchange_keys(keys, method)
+            if int(tot_all[:, plan.bins, 0].max().item()) == 0:   # every rank verified its candidates (same answer on all ranks)
+                return keys
         hist = st.hist(plan, qp, None, gp_local, None, **kw)
         if method == "allgather_merge":
             sc = st.scan(plan, hist, 1, 0, k, with_rel=False)      # local ranking of this shard
@@ -512,5 +608,9 @@ class ShardedEvaluator:
         totals_all = self._gather(st.hist_totals(plan, hist))      # [world, 2, bins, Qpad]
         sc = st.scan_sharded(plan, hist, totals_all, self.world, self.rank, k)
         keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset, **kw)  # slots of global rank < k owned by this shard
-        self.dist.all_reduce(keys, op=self.dist.ReduceOp.MAX, group=self.group)   # EMPTY = -1 < every real key
+        self._exchange_keys(keys, method)
         return keys
+
+    def _exchange_keys(self, keys: torch.Tensor, method: str) -> None:
+        """Every slot of the [Q, k] key buffer is owned by exactly one rank (the others hold EMPTY = -1 < every real key)."""
+        self.dist.all_reduce(keys, op=self.dist.ReduceOp.MAX, group=self.group)

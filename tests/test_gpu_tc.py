@@ -114,3 +114,61 @@ def test_tc_many_shared_classes_do_not_leak_into_the_distance():
 
 def test_tc_is_the_default_path():
     assert R.CudaStages().tensor_cores is True
+
+
+# ---- candidate path of the top-k ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K", [16, 32, 64, 128])
+@pytest.mark.parametrize("k", [1, 100, 1000])
+def test_candidate_topk_equals_exact_two_pass(K, k):
+    Q, N = 700, 300_000
+    qp = R.pack_codes(synth.random_codes(Q, K, 100 + K).to(DEV))
+    gp = R.pack_codes(synth.random_codes(N, K, 101 + K).to(DEV))
+    st = R.CudaStages(True)
+    assert R.candidate_path_ok(st, st.make_plan(Q, N, K, 0), N, k)
+    stages = []
+    fast = R.topk(qp, gp, K, k, idx_offset=5, stages=stages)
+    assert len(stages) == len(R.TOPK_FAST_STAGE_NAMES)        # i.i.d. codes: the candidate path verified and returned
+    exact = R.topk(qp, gp, K, k, idx_offset=5, exact=True)
+    assert torch.equal(fast, exact)
+
+
+def test_candidate_topk_clustered_codes_and_fallback():
+    """clustered codes: huge tie buckets at small distances (lists overflow -> verified fallback); result must not change."""
+    Q, N, K, k = 256, 262_144, 64, 500
+    qp = R.pack_codes(synth.clustered_codes(Q, K, 5).to(DEV))
+    gp = R.pack_codes(synth.clustered_codes(N, K, 6).to(DEV))
+    assert torch.equal(R.topk(qp, gp, K, k), R.topk(qp, gp, K, k, exact=True))
+    # a gallery whose prefix looks nothing like the rest: the sampled cutoffs are far too tight -> detected, exact path
+    far = synth.random_codes(N, K, 7)
+    near = synth.random_codes(1, K, 8).expand(40_000, K)
+    g2 = torch.cat([far[: N - 40_000], near]).contiguous()
+    q2 = torch.cat([synth.random_codes(1, K, 8).expand(100, K), synth.random_codes(Q - 100, K, 9)]).contiguous()
+    qp2, gp2 = R.pack_codes(q2.to(DEV)), R.pack_codes(g2.to(DEV))
+    assert torch.equal(R.topk(qp2, gp2, K, k), R.topk(qp2, gp2, K, k, exact=True))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_candidate_stages_sharded_equal_single(world):
+    """the sharded form of the candidate path, simulated on one GPU: per-shard collect + count, totals concatenated like the
+    all-gather, per-shard place into one key buffer == single-GPU keys."""
+    Q, N, K, k = 300, 400_000, 64, 1000
+    qp = R.pack_codes(synth.random_codes(Q, K, 1).to(DEV))
+    gp = R.pack_codes(synth.random_codes(N, K, 2).to(DEV))
+    want = R.topk(qp, gp, K, k, exact=True)
+    st = R.CudaStages(True)
+    bounds = R.shard_bounds(N, world)
+    n_geom = max(hi - lo for lo, hi in bounds)
+    parts = []
+    for lo, hi in bounds:
+        plan = st.make_plan(Q, hi - lo, K, 0, n_geom)
+        ops = st.operands(plan, qp, None, gp[lo:hi], None)
+        parts.append((plan, lo) + R.collect_candidates(st, plan, ops, qp, gp[lo:hi], k))
+    tot_all = torch.stack([p[5] for p in parts]).contiguous()
+    assert int(tot_all[:, parts[0][0].bins, 0].max()) == 0
+    keys = torch.full((Q, k), R.EMPTY_KEY, dtype=torch.int64, device=DEV)
+    for r, (plan, lo, cap, cand, cnt, tot) in enumerate(parts):
+        mine = torch.full((Q, k), R.EMPTY_KEY, dtype=torch.int64, device=DEV)
+        st.topk_place(plan, cap, cand, cnt, tot_all, world, r, k, lo, mine)
+        assert int(((mine != R.EMPTY_KEY) & (keys != R.EMPTY_KEY)).sum()) == 0   # every slot has exactly one owner
+        keys = torch.maximum(keys, mine)
+    assert torch.equal(keys, want)
