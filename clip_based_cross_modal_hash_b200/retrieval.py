@@ -313,18 +313,20 @@ class CudaStages:
 
     # ---- candidate path of the top-k (cmh_tc_topk_*) ----
     def topk_cutoff(self, plan_s: Plan, hist_s: torch.Tensor, n_local: int, k: int) -> torch.Tensor:
-        cutoff = torch.empty(plan_s.Qpad, dtype=torch.int32, device=hist_s.device)
+        """-> int32 [2, Qpad]: row 0 = cutoff distance T, row 1 = shard-index bound for bucket T."""
+        cut = torch.empty((2, plan_s.Qpad), dtype=torch.int32, device=hist_s.device)
         with torch.cuda.device(hist_s.device):
-            check(_lib.lib().cmh_tc_topk_cutoff(ctypes.byref(plan_s), hist_s.data_ptr(), n_local, k, cutoff.data_ptr(), _stream()))
-        return cutoff
+            check(_lib.lib().cmh_tc_topk_cutoff(ctypes.byref(plan_s), hist_s.data_ptr(), n_local, k, cut[0].data_ptr(),
+                                                cut[1].data_ptr(), _stream()))
+        return cut
 
     def topk_collect(self, plan: Plan, ops: Operands, cutoff: torch.Tensor, cap: int) -> Tuple[torch.Tensor, torch.Tensor]:
         dev = cutoff.device
         cand = torch.empty((plan.nchunks, plan.Qpad, cap), dtype=torch.int32, device=dev)
         cnt = torch.empty((plan.nchunks, plan.Qpad), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            check(_lib.lib().cmh_tc_topk_collect(ctypes.byref(plan), ctypes.byref(ops.c), cutoff.data_ptr(), cap, cand.data_ptr(),
-                                                 cnt.data_ptr(), _stream()))
+            check(_lib.lib().cmh_tc_topk_collect(ctypes.byref(plan), ctypes.byref(ops.c), cutoff[0].data_ptr(), cutoff[1].data_ptr(),
+                                                 cap, cand.data_ptr(), cnt.data_ptr(), _stream()))
         return cand, cnt
 
     def topk_count(self, plan: Plan, cap: int, cand: torch.Tensor, cnt: torch.Tensor, k: int) -> torch.Tensor:
@@ -406,7 +408,7 @@ def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None):
         hist_s = st.hist(plan_s, qp, None, gp[:n_s], None, ops=ops)
         cutoff = st.topk_cutoff(plan_s, hist_s, plan.N, k)
     else:   # an empty shard has no candidates
-        cutoff = torch.full((plan.Qpad,), -1, dtype=torch.int32, device=qp.device)
+        cutoff = torch.full((2, plan.Qpad), -1, dtype=torch.int32, device=qp.device)
     _mark(stages)
     cap = candidate_cap(plan, k)
     cand, cnt = st.topk_collect(plan, ops, cutoff, cap)

@@ -198,16 +198,19 @@ int cmh_tc_rank_map(const cmh_plan* plan, const cmh_tc_operands* ops, const uint
 /* Candidate path of the top-k (what retrieval.topk runs by default on large galleries; the two-pass path above is its exact
  * fallback).  Only ~k of N items can be in a query's top-k: with a per-query cutoff distance T >= (distance of the k-th
  * neighbour) ONE tensor-core pass appends the items with d <= T to per-(chunk, query) lists and skips everything else.
- *   cmh_tc_topk_cutoff   T[q] from the exact histogram (cmh_tc_hist on `sample_plan`) of a gallery prefix, 5-sigma margin
+ *   cmh_tc_topk_cutoff   cutoff T[q] and index bound I[q] from the exact histogram (cmh_tc_hist on `sample_plan`) of a gallery
+ *                        prefix, 5-sigma margin: candidates = { d < T } + { d == T, shard index <= I (rounded up to a 64-item tile) },
+ *                        a prefix of the stable (distance, index) order
  *   cmh_tc_topk_collect  cand[c][q][cand_cap] = (distance << 24) | index inside chunk c, in gallery order; cand_count[c][q]
+ *                        (0xFFFFFFFF = the list overflowed)
  *   cmh_tc_topk_count    totals[d][q] = #candidates at distance d ([bins][Qpad], what a rank exchanges); flags[0] |= 1 if a
  *                        list overflowed or a query has fewer than min(k, N) candidates -> caller must use the exact path
  *   cmh_tc_topk_place    keys[q][rank] for this shard's candidates with global stable rank < k; totals_all = the all-gathered
  *                        totals, rank r's [bins][Qpad] block starting at r * rank_stride elements */
 int cmh_tc_topk_cutoff(const cmh_plan* sample_plan, const uint32_t* hist_sample, int64_t n_local, int64_t k, int32_t* cutoff,
-                       void* stream);
-int cmh_tc_topk_collect(const cmh_plan* plan, const cmh_tc_operands* ops, const int32_t* cutoff, int cand_cap, uint32_t* cand,
-                        uint32_t* cand_count, void* stream);
+                       int32_t* ibound, void* stream);
+int cmh_tc_topk_collect(const cmh_plan* plan, const cmh_tc_operands* ops, const int32_t* cutoff, const int32_t* ibound,
+                        int cand_cap, uint32_t* cand, uint32_t* cand_count, void* stream);
 int cmh_tc_topk_count(const cmh_plan* plan, int cand_cap, const uint32_t* cand, const uint32_t* cand_count, int64_t k,
                       uint32_t* totals, int32_t* flags, void* stream);
 int cmh_tc_topk_place(const cmh_plan* plan, int cand_cap, const uint32_t* cand, const uint32_t* cand_count,
