@@ -335,6 +335,8 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
     if world == 1 and want_stage and stage_ms is not None:
         names = R.TOPK_FAST_STAGE_NAMES if len(stage_ms) == 7 else R.TOPK_STAGE_NAMES
         out["stage_ms"] = {"pack": stage_ms[0] / steps, **{n: v / steps for n, v in zip(names, stage_ms[1:])}}
+    if ev is not None:
+        out["exchange_info"] = ev.exchange_info()
     n_local = hi - lo
     out["survey_8d"] = survey_roofline(Q, n_local, K, k, out["ms_per_step"], peaks, out["clocks"].get("sm_mhz"))
 
@@ -668,7 +670,7 @@ def run_ours(args, cfg, name):
         "l2": "256 MiB flush write between timed steps",
     }
     if args.op == "topk":
-        line["exchange"] = args.topk_exchange if world > 1 else None
+        line["exchange"] = {"method": args.topk_exchange, **head.get("exchange_info", {})} if world > 1 else None
         line["parity_check"] = head.get("parity_check")
         dom, dom_ms = None, None
         if "stage_ms" in head:

@@ -15,6 +15,7 @@ code buffers / all-reduce of ``runners/base.py:242-266``.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -339,10 +340,14 @@ class CudaStages:
         return tot
 
     def topk_place(self, plan: Plan, cap: int, cand: torch.Tensor, cnt: torch.Tensor, totals_all: torch.Tensor, world: int,
-                   rank: int, k: int, idx_offset: int, keys: torch.Tensor) -> torch.Tensor:
+                   rank: int, k: int, idx_offset: int, keys: Optional[torch.Tensor], peers_dev: Optional[int] = None, npeers: int = 0,
+                   multicast: Optional[int] = None) -> Optional[torch.Tensor]:
+        """``peers_dev``: device address of a table of ``npeers`` peer-mapped [Q, k] key buffers (one per rank); ``multicast``: the
+        NVSwitch multicast address of those buffers.  With either, the keys go straight into every rank's buffer."""
         with torch.cuda.device(cand.device):
             check(_lib.lib().cmh_tc_topk_place(ctypes.byref(plan), cap, cand.data_ptr(), cnt.data_ptr(), totals_all.data_ptr(),
-                                               (plan.bins + 1) * plan.Qpad, world, rank, k, idx_offset, keys.data_ptr(), _stream()))
+                                               (plan.bins + 1) * plan.Qpad, world, rank, k, idx_offset, _ptr(keys), peers_dev, npeers,
+                                               multicast, _stream()))
         return keys
 
     def topk_merge(self, parts: torch.Tensor) -> torch.Tensor:
@@ -533,6 +538,51 @@ class ShardedEvaluator:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.stages = stages if stages is not None else CudaStages()
+        self.use_multicast = os.environ.get("CMH_NO_MULTICAST", "0") in ("", "0")
+        self._symm = {}          # (Q, k, device) -> (tensor, handle) symmetric [Q, k] key buffers of the fused exchange
+        self._symm_broken = None  # reason symmetric memory is unusable in this process group, once known
+
+    # ---- fused exchange: every rank's [Q, k] key buffer is mapped into every other rank (NVLink / NVSwitch) ----
+    def _symmetric_keys(self, Q: int, k: int, device):
+        """Symmetric-memory [Q, k] int64 buffer + its rendezvous handle (cached per shape); None when this build / box / group
+        cannot map peer memory (then the all-reduce exchange is used).  Collective: every rank must call it with the same shape."""
+        if self._symm_broken is not None or device.type != "cuda":
+            return None
+        key = (Q, k, device.index)
+        if key not in self._symm:
+            buf, err = None, None
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                buf = symm_mem.empty((Q, k), dtype=torch.int64, device=device)
+            except Exception as e:
+                err = "%s: %s" % (type(e).__name__, e)
+            # the allocation is local, the rendezvous is collective: agree first so that no rank waits for one that gave up
+            ok = torch.tensor([0 if buf is None else 1], dtype=torch.int32, device=device)
+            self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self._symm_broken = err or "symmetric memory allocation failed on another rank"
+                return None
+            try:
+                grp = self.group if self.group is not None else self.dist.group.WORLD
+                hdl = symm_mem.rendezvous(buf, grp)
+                if len(hdl.buffer_ptrs) != self.world:
+                    raise RuntimeError("rendezvous returned %d buffers for %d ranks" % (len(hdl.buffer_ptrs), self.world))
+                self._symm[key] = (buf, hdl)
+            except Exception as e:  # not supported here: remember why, use the NCCL exchange from now on
+                self._symm_broken = "%s: %s" % (type(e).__name__, e)
+                return None
+        return self._symm[key]
+
+    def exchange_info(self) -> Dict[str, object]:
+        """What the top-k exchange uses in this process group (for logs / bench.py)."""
+        if self._symm_broken is not None:
+            return {"peer_memory": False, "reason": self._symm_broken[:200]}
+        if not self._symm:
+            return {"peer_memory": None}
+        hdl = next(iter(self._symm.values()))[1]
+        mc = bool(getattr(hdl, "has_multicast_support", False)) and bool(getattr(hdl, "multicast_ptr", 0))
+        return {"peer_memory": True, "multicast": mc}
 
     def _gather(self, t: torch.Tensor) -> torch.Tensor:
         t = t.contiguous()
@@ -570,7 +620,7 @@ class ShardedEvaluator:
         return MapResult(m, ap, sc["tsum"][:Q], sc["total"][:Q], tindex)
 
     def topk(self, qp, gp_local, nbits: int, k: int, idx_offset: int, n_geom: Optional[int] = None,
-             method: str = "auto", exact: Optional[bool] = None) -> torch.Tensor:
+             method: str = "auto", exact: Optional[bool] = None, copy: bool = True) -> torch.Tensor:
         """Global top-k keys [Q, k] (identical on every rank) of a gallery sharded by contiguous index range.
 
         ``rank_scatter`` (default): the counting formulation gives every item its GLOBAL stable rank from this rank's own
@@ -582,8 +632,6 @@ class ShardedEvaluator:
         """
         st = self.stages
         k = _check_k(k)
-        if method == "auto":
-            method = "rank_scatter"
         Q, n_local = qp.shape[0], gp_local.shape[0]
         n_geom = self._geometry(n_local, n_geom, qp.device)
         plan = st.make_plan(Q, n_local, nbits, 0, n_geom)
@@ -594,12 +642,31 @@ class ShardedEvaluator:
             # candidate path: local cutoffs guarantee >= min(k, n_local) LOCAL candidates, hence every item of the global top-k
             cap, cand, cnt, tot = collect_candidates(st, plan, ops, qp, gp_local, k)
             tot_all = self._gather(tot)                            # [world, bins + 1, Qpad]: per-distance totals + fallback flag
-            keys = torch.full((Q, k), EMPTY_KEY, dtype=torch.int64, device=qp.device)
-            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys)
-            self._exchange_keys(keys, method)
+            symm = self._symmetric_keys(Q, k, qp.device) if method in ("auto", "peer_scatter") else None
+            if method == "peer_scatter" and symm is None:
+                raise CmhError("peer_scatter exchange is not available: %s" % self._symm_broken)
+            if symm is not None:
+                # ONE kernel places AND exchanges: a key's global slot is known, so it is stored straight into that slot of every
+                # rank's buffer (multimem.st through the switch, or one NVLink store per peer).  Barriers: peers must be done
+                # reading the previous result before anyone overwrites it, and all stores must have landed before anyone reads.
+                buf, hdl = symm
+                if k > n_geom * self.world:
+                    buf.fill_(EMPTY_KEY)
+                hdl.barrier(channel=0)
+                mc = int(hdl.multicast_ptr) if (getattr(hdl, "has_multicast_support", False) and self.use_multicast) else 0
+                st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, None,
+                              peers_dev=int(hdl.buffer_ptrs_dev), npeers=self.world, multicast=mc or None)
+                hdl.barrier(channel=1)
+                keys = buf.clone() if copy else buf
+            else:
+                keys = torch.full((Q, k), EMPTY_KEY, dtype=torch.int64, device=qp.device)
+                st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys)
+                self._exchange_keys(keys, method)
             if int(tot_all[:, plan.bins, 0].max().item()) == 0:   # every rank verified its candidates (same answer on all ranks)
                 return keys
         hist = st.hist(plan, qp, None, gp_local, None, **kw)
+        if method in ("auto", "peer_scatter"):
+            method = "rank_scatter"                                 # the exact two-pass path exchanges through NCCL
         if method == "allgather_merge":
             sc = st.scan(plan, hist, 1, 0, k, with_rel=False)      # local ranking of this shard
             keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset, **kw)

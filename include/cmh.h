@@ -206,7 +206,12 @@ int cmh_tc_rank_map(const cmh_plan* plan, const cmh_tc_operands* ops, const uint
  *   cmh_tc_topk_count    totals[d][q] = #candidates at distance d ([bins][Qpad], what a rank exchanges); flags[0] |= 1 if a
  *                        list overflowed or a query has fewer than min(k, N) candidates -> caller must use the exact path
  *   cmh_tc_topk_place    keys[q][rank] for this shard's candidates with global stable rank < k; totals_all = the all-gathered
- *                        totals, rank r's [bins][Qpad] block starting at r * rank_stride elements */
+ *                        totals, rank r's [bins][Qpad] block starting at r * rank_stride elements.
+ *                        Fused exchange (replaces the all-reduce of the [Q][k] buffer): with multicast_keys != NULL every key is
+ *                        stored once through that NVSwitch multicast address (multimem.st) and lands in the same slot of every
+ *                        rank's buffer; else with npeers > 0, peer_keys = DEVICE array of npeers buffer addresses (one per rank,
+ *                        peer-mapped) and the kernel stores the key into each of them over NVLink; else into `keys`.
+ *                        The caller owns the synchronisation (a barrier over the ranks before and after). */
 int cmh_tc_topk_cutoff(const cmh_plan* sample_plan, const uint32_t* hist_sample, int64_t n_local, int64_t k, int32_t* cutoff,
                        int32_t* ibound, void* stream);
 int cmh_tc_topk_collect(const cmh_plan* plan, const cmh_tc_operands* ops, const int32_t* cutoff, const int32_t* ibound,
@@ -215,7 +220,7 @@ int cmh_tc_topk_count(const cmh_plan* plan, int cand_cap, const uint32_t* cand, 
                       uint32_t* totals, int32_t* flags, void* stream);
 int cmh_tc_topk_place(const cmh_plan* plan, int cand_cap, const uint32_t* cand, const uint32_t* cand_count,
                       const uint32_t* totals_all, int64_t rank_stride, int world, int rank, int64_t k, int64_t idx_offset,
-                      uint64_t* keys, void* stream);
+                      uint64_t* keys, const uint64_t* peer_keys, int npeers, uint64_t* multicast_keys, void* stream);
 
 /* ---- R5: merge of per-shard partial top-k after ONE all-gather -----------------------------------------
  * parts = [world][Q][k] sorted keys (0xFFFF...F = empty slot); out[q] = the k smallest keys. */

@@ -27,7 +27,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ev = R.ShardedEvaluator()
     ok = True
-    for (Q, N, K, C, k) in [(300, 20011, 64, 80, None), (257, 50000, 128, 21, 500), (1000, 200000, 32, 24, 1000)]:
+    for (Q, N, K, C, k) in [(300, 20011, 64, 80, None), (257, 50000, 128, 21, 500), (1000, 200000, 32, 24, 1000),
+                            (700, 150000 * world, 64, 80, 1000)]:   # last: every shard large enough for the candidate path
         qB, rB = synth.random_codes(Q, K, 1), synth.random_codes(N, K, 2)
         qL, rL = synth.random_labels(Q, C, 3), synth.random_labels(N, C, 4)
         qp, gp = R.pack_codes(qB.to(dev)), R.pack_codes(rB.to(dev))
@@ -39,8 +40,11 @@ def main():
         keys1 = R.topk(qp, gp, K, kk)
         keys = ev.topk(qp, gp[lo:hi], K, kk, lo)
         keys_ag = ev.topk(qp, gp[lo:hi], K, kk, lo, method="allgather_merge")
+        keys_rs = ev.topk(qp, gp[lo:hi], K, kk, lo, method="rank_scatter")
+        keys_ex = ev.topk(qp, gp[lo:hi], K, kk, lo, exact=True)
         good = (torch.equal(res.tindex, single.tindex) and torch.equal(res.total, single.total)
-                and abs(res.map.item() - single.map.item()) < 1e-12 and torch.equal(keys, keys1) and torch.equal(keys_ag, keys1))
+                and abs(res.map.item() - single.map.item()) < 1e-12 and torch.equal(keys, keys1) and torch.equal(keys_ag, keys1)
+                and torch.equal(keys_rs, keys1) and torch.equal(keys_ex, keys1))
         if rank == 0:
             from oracle import c_oracle, hamming_oracle as ho
             W = (K + 31) // 32
@@ -50,6 +54,19 @@ def main():
             good = good and np.array_equal(res.tindex.cpu().numpy()[sub], tix)
             print("Q=%d N=%d K=%d k=%s world=%d: %s  mAP=%.9f" % (Q, N, K, k, world, "OK" if good else "MISMATCH", res.map.item()), flush=True)
         ok = ok and good
+    # the fused exchange of the candidate path: multicast stores (when the box has NVLS) and plain peer stores
+    Q, N, K, kk = 900, 120000 * world, 64, 1000
+    qp, gp = R.pack_codes(synth.random_codes(Q, K, 5).to(dev)), R.pack_codes(synth.random_codes(N, K, 6).to(dev))
+    lo, hi = R.shard_bounds(N, world)[rank]
+    want = R.topk(qp, gp, K, kk, exact=True)
+    outs = {}
+    for name, mc in (("auto", True), ("peer stores", False)):
+        ev.use_multicast = mc
+        outs[name] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo), want))
+    ev.use_multicast = True
+    if rank == 0:
+        print("fused exchange world=%d: %s  %s" % (world, outs, ev.exchange_info()), flush=True)
+    ok = ok and all(outs.values())
     # get_code's distributed merge of packed code buffers (byte-wise MAX over NCCL), with DistributedSampler-style padding
     from clip_based_cross_modal_hash_b200 import models
     g = torch.Generator().manual_seed(0)
