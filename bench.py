@@ -42,6 +42,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # the version banner goes to stdout and would precede the JSON line
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 from clip_based_cross_modal_hash_b200 import synth  # noqa: E402
 
@@ -294,7 +296,7 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
         qp, gp = R.pack_codes(d_qB), R.pack_codes(d_rB)
         mark()
         if world > 1:
-            keys = ev.topk(qp, gp, K, k, lo, n_geom=n_geom, method=args.topk_exchange)
+            keys = ev.topk(qp, gp, K, k, lo, n_geom=n_geom, method=args.topk_exchange, stages=events)
             mark()
             return keys
         keys = R.topk(qp, gp, K, k, stages=events, out=keys_buf)
@@ -306,18 +308,20 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
         flush.zero_()
     D.barrier()
     l0 = launches()
-    per_step, stage_ms = [], None
+    per_step, stage_ms, host_ms = [], None, 0.0
     with ClockSampler(D.local_rank) as clocks:
         D.barrier()
         for _ in range(steps):
             flush.zero_()
             evs = []
+            h0 = time.perf_counter()
             keys = step(evs)
+            host_ms += (time.perf_counter() - h0) * 1e3     # host time to queue one step (launch-bound if close to ms_per_step)
             torch.cuda.synchronize()
             per_step.append(evs[0].elapsed_time(evs[-1]))
-            if world == 1 and want_stage:
+            if want_stage:
                 d = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]
-                stage_ms = d if stage_ms is None else [a + b for a, b in zip(stage_ms, d)]
+                stage_ms = d if (stage_ms is None or len(stage_ms) != len(d)) else [a + b for a, b in zip(stage_ms, d)]
         D.barrier()
     n_launch = launches() - l0
     total_ms = D.all_max(sum(per_step))
@@ -332,9 +336,13 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
         chk["equal_on_every_rank"] = ok
         out["parity_check"] = chk
         del gp_full
-    if world == 1 and want_stage and stage_ms is not None:
-        names = R.TOPK_FAST_STAGE_NAMES if len(stage_ms) == 7 else R.TOPK_STAGE_NAMES
+    if want_stage and stage_ms is not None:
+        if world > 1:
+            names = R.TOPK_SHARDED_STAGE_NAMES if len(stage_ms) == 8 else tuple("stage%d" % i for i in range(len(stage_ms)))
+        else:
+            names = R.TOPK_FAST_STAGE_NAMES if len(stage_ms) == 7 else R.TOPK_STAGE_NAMES
         out["stage_ms"] = {"pack": stage_ms[0] / steps, **{n: v / steps for n, v in zip(names, stage_ms[1:])}}
+        out["host_ms_per_step"] = host_ms / steps
     if ev is not None:
         out["exchange_info"] = ev.exchange_info()
     n_local = hi - lo
@@ -675,6 +683,7 @@ def run_ours(args, cfg, name):
         dom, dom_ms = None, None
         if "stage_ms" in head:
             line["stage_ms"] = head["stage_ms"]
+            line["host_ms_per_step"] = head.get("host_ms_per_step")
             dom, dom_ms = max(((n, v) for n, v in head["stage_ms"].items()), key=lambda x: x[1])
         s8 = head["survey_8d"]
         kern_ms = dom_ms if dom_ms is not None else head["ms_per_step"]
@@ -739,7 +748,7 @@ def main():
     ap.add_argument("--workload", default="C4-64", choices=sorted(synth.CONFIGS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="top-k only: strong = the workload's gallery split over the GPUs (default), weak = one full gallery per GPU")
-    ap.add_argument("--topk-exchange", default="auto", choices=["auto", "peer_scatter", "rank_scatter", "allgather_merge"])
+    ap.add_argument("--topk-exchange", default="auto", choices=["auto", "nvls", "peer_stores", "rank_scatter", "allgather_merge"])
     ap.add_argument("--no-encode", action="store_true", help="skip the CLIP encode section of the line")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 16/32/128-bit sweep")
     ap.add_argument("--no-c2", action="store_true", help="skip the C2 mAP object")

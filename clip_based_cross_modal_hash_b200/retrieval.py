@@ -383,6 +383,7 @@ class MapResult:
 
 TOPK_STAGE_NAMES = ("expand", "hist_kernel", "scan", "rank_topk_kernel")                       # exact two-pass path
 TOPK_FAST_STAGE_NAMES = ("expand", "sample_hist+cutoff", "collect_kernel", "count", "place")  # candidate path
+TOPK_SHARDED_STAGE_NAMES = ("expand", "sample_hist+cutoff", "collect_kernel", "count", "gather_totals", "place+nvls_allreduce")
 CAND_MIN_ITEMS = 65536   # shards smaller than this take the two-pass path directly
 
 
@@ -538,7 +539,6 @@ class ShardedEvaluator:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.stages = stages if stages is not None else CudaStages()
-        self.use_multicast = os.environ.get("CMH_NO_MULTICAST", "0") in ("", "0")
         self._symm = {}          # (Q, k, device) -> (tensor, handle) symmetric [Q, k] key buffers of the fused exchange
         self._symm_broken = None  # reason symmetric memory is unusable in this process group, once known
 
@@ -568,6 +568,8 @@ class ShardedEvaluator:
                 hdl = symm_mem.rendezvous(buf, grp)
                 if len(hdl.buffer_ptrs) != self.world:
                     raise RuntimeError("rendezvous returned %d buffers for %d ranks" % (len(hdl.buffer_ptrs), self.world))
+                if not (getattr(hdl, "has_multicast_support", False) and int(hdl.multicast_ptr)):
+                    raise RuntimeError("no NVSwitch multicast mapping for the key buffer (NVLS unavailable)")
                 self._symm[key] = (buf, hdl)
             except Exception as e:  # not supported here: remember why, use the NCCL exchange from now on
                 self._symm_broken = "%s: %s" % (type(e).__name__, e)
@@ -620,7 +622,7 @@ class ShardedEvaluator:
         return MapResult(m, ap, sc["tsum"][:Q], sc["total"][:Q], tindex)
 
     def topk(self, qp, gp_local, nbits: int, k: int, idx_offset: int, n_geom: Optional[int] = None,
-             method: str = "auto", exact: Optional[bool] = None, copy: bool = True) -> torch.Tensor:
+             method: str = "auto", exact: Optional[bool] = None, copy: bool = True, stages: Optional[list] = None) -> torch.Tensor:
         """Global top-k keys [Q, k] (identical on every rank) of a gallery sharded by contiguous index range.
 
         ``rank_scatter`` (default): the counting formulation gives every item its GLOBAL stable rank from this rank's own
@@ -636,28 +638,45 @@ class ShardedEvaluator:
         n_geom = self._geometry(n_local, n_geom, qp.device)
         plan = st.make_plan(Q, n_local, nbits, 0, n_geom)
         ops = st.operands(plan, qp, None, gp_local, None) if hasattr(st, "operands") else None
+        _mark(stages)
         kw = {"ops": ops} if ops is not None else {}
         if (method != "allgather_merge" and exact is not True and ops is not None
                 and candidate_path_ok(st, plan, n_geom, k)):   # decided on the common geometry: same path on every rank
             # candidate path: local cutoffs guarantee >= min(k, n_local) LOCAL candidates, hence every item of the global top-k
-            cap, cand, cnt, tot = collect_candidates(st, plan, ops, qp, gp_local, k)
+            cap, cand, cnt, tot = collect_candidates(st, plan, ops, qp, gp_local, k, stages)
             tot_all = self._gather(tot)                            # [world, bins + 1, Qpad]: per-distance totals + fallback flag
-            symm = self._symmetric_keys(Q, k, qp.device) if method in ("auto", "peer_scatter") else None
-            if method == "peer_scatter" and symm is None:
-                raise CmhError("peer_scatter exchange is not available: %s" % self._symm_broken)
-            if symm is not None:
-                # ONE kernel places AND exchanges: a key's global slot is known, so it is stored straight into that slot of every
-                # rank's buffer (multimem.st through the switch, or one NVLink store per peer).  Barriers: peers must be done
-                # reading the previous result before anyone overwrites it, and all stores must have landed before anyone reads.
+            _mark(stages)
+            symm = self._symmetric_keys(Q, k, qp.device) if method in ("auto", "nvls", "peer_stores") else None
+            if method in ("nvls", "peer_stores") and symm is None:
+                raise CmhError("%s exchange is not available: %s" % (method, self._symm_broken))
+            if symm is not None and method == "peer_stores":
+                # fused place + exchange: a key's global slot is known, so the place kernel stores it straight into that slot of
+                # every rank's buffer over NVLink.  Correct, but scattered 8-byte remote stores run at a fraction of the link rate
+                # (2 GPUs: 0.69 ms against 0.16 ms local placement + 0.1 ms NVLS reduction, profiles/README.md): not the default.
                 buf, hdl = symm
                 if k > n_geom * self.world:
                     buf.fill_(EMPTY_KEY)
                 hdl.barrier(channel=0)
-                mc = int(hdl.multicast_ptr) if (getattr(hdl, "has_multicast_support", False) and self.use_multicast) else 0
                 st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, None,
-                              peers_dev=int(hdl.buffer_ptrs_dev), npeers=self.world, multicast=mc or None)
+                              peers_dev=int(hdl.buffer_ptrs_dev), npeers=self.world)
                 hdl.barrier(channel=1)
                 keys = buf.clone() if copy else buf
+                _mark(stages)
+            elif symm is not None:
+                # The keys are placed into this rank's symmetric buffer (slots owned by other ranks stay EMPTY); then ONE kernel per
+                # rank reduces 1/world of the buffer in the switch (multimem.ld_reduce max) and broadcasts it (multimem.st).
+                # Barriers: peers must be done with the previous result before it is overwritten; all fills + placements must be
+                # visible before the reduction; all broadcasts must have landed before anyone reads.
+                buf, hdl = symm
+                hdl.barrier(channel=0)
+                buf.fill_(EMPTY_KEY)
+                st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf)
+                hdl.barrier(channel=1)
+                with torch.cuda.device(qp.device):
+                    check(_lib.lib().cmh_nvls_allreduce_max_s64(int(hdl.multicast_ptr), buf.numel(), self.rank, self.world, _stream()))
+                hdl.barrier(channel=2)
+                keys = buf.clone() if copy else buf
+                _mark(stages)
             else:
                 keys = torch.full((Q, k), EMPTY_KEY, dtype=torch.int64, device=qp.device)
                 st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys)
@@ -665,7 +684,7 @@ class ShardedEvaluator:
             if int(tot_all[:, plan.bins, 0].max().item()) == 0:   # every rank verified its candidates (same answer on all ranks)
                 return keys
         hist = st.hist(plan, qp, None, gp_local, None, **kw)
-        if method in ("auto", "peer_scatter"):
+        if method in ("auto", "nvls", "peer_stores"):
             method = "rank_scatter"                                 # the exact two-pass path exchanges through NCCL
         if method == "allgather_merge":
             sc = st.scan(plan, hist, 1, 0, k, with_rel=False)      # local ranking of this shard

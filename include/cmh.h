@@ -222,6 +222,14 @@ int cmh_tc_topk_place(const cmh_plan* plan, int cand_cap, const uint32_t* cand, 
                       const uint32_t* totals_all, int64_t rank_stride, int world, int rank, int64_t k, int64_t idx_offset,
                       uint64_t* keys, const uint64_t* peer_keys, int npeers, uint64_t* multicast_keys, void* stream);
 
+/* ---- X: the exchange step of the sharded top-k through NVSwitch multicast memory (NVLS) -------------------------------
+ * `multicast_ptr` = the multicast address of a symmetric int64 buffer of `count` elements that every rank of the group has
+ * mapped (torch.distributed._symmetric_memory: handle.multicast_ptr).  Rank `rank` reduces its 1/world slice with
+ * multimem.ld_reduce(max.s64) — the switch reads the slot on every rank — and broadcasts the result with multimem.st, so after
+ * a barrier every rank's buffer holds the element-wise maximum.  Replaces the NCCL all-reduce(MAX) of the [Q][k] key buffer
+ * (unowned slots are -1).  The caller brackets the call with barriers over the ranks. */
+int cmh_nvls_allreduce_max_s64(void* multicast_ptr, int64_t count, int rank, int world, void* stream);
+
 /* ---- R5: merge of per-shard partial top-k after ONE all-gather -----------------------------------------
  * parts = [world][Q][k] sorted keys (0xFFFF...F = empty slot); out[q] = the k smallest keys. */
 int cmh_topk_merge(const uint64_t* parts, int world, int64_t Q, int64_t k, uint64_t* out, void* stream);

@@ -60,10 +60,10 @@ def main():
     lo, hi = R.shard_bounds(N, world)[rank]
     want = R.topk(qp, gp, K, kk, exact=True)
     outs = {}
-    for name, mc in (("auto", True), ("peer stores", False)):
-        ev.use_multicast = mc
-        outs[name] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo), want))
-    ev.use_multicast = True
+    outs["auto"] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo), want))
+    outs["auto, zero-copy result"] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo, copy=False), want))
+    if ev.exchange_info().get("peer_memory"):
+        outs["peer_stores"] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo, method="peer_stores"), want))
     if rank == 0:
         print("fused exchange world=%d: %s  %s" % (world, outs, ev.exchange_info()), flush=True)
     ok = ok and all(outs.values())
