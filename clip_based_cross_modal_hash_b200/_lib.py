@@ -17,7 +17,7 @@ INCLUDE = os.path.join(ROOT, "include")
 SO_PATH = os.path.join(_HERE, "libcmh.so")
 
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 

@@ -145,6 +145,19 @@ def hamming_dense(b1: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------------
 # evaluator stages (one C entry point each)
 # ---------------------------------------------------------------------------------------------------------
+TC_BLOCKS_PER_SM = int(os.environ.get("CMH_TC_BLOCKS_PER_SM", "0"))   # 0 = the library default (16); measured flat between 4 and 16
+_SM_COUNT = None
+
+
+def _sm_count() -> int:
+    global _SM_COUNT
+    if _SM_COUNT is None:
+        sm = ctypes.c_int(0)
+        rc = _lib.lib().cmh_device_info(ctypes.byref(sm), None, None) if torch.cuda.is_available() else -1
+        _SM_COUNT = sm.value if rc == 0 and sm.value > 0 else 148
+    return _SM_COUNT
+
+
 class Operands:
     """int8 operand rows of the tensor-core ranking passes (``cmh_tc_*``), expanded once per evaluation from the packed words and
     shared by the histogram and the rank pass.  Holds the device buffers alive."""
@@ -179,6 +192,8 @@ class CudaStages:
         self.tensor_cores = bool(tensor_cores)
 
     def make_plan(self, Q, N, nbits, ncls, N_geom=None, target_blocks=0) -> Plan:
+        if target_blocks == 0 and self.tensor_cores and TC_BLOCKS_PER_SM > 0:   # tuning knob (scripts/sweep_blocks.sh)
+            target_blocks = TC_BLOCKS_PER_SM * _sm_count()
         return _lib.make_plan(Q, N, nbits, ncls, N_geom, target_blocks)
 
     def operands(self, plan: Plan, qp, qlp, gp, glp) -> Optional[Operands]:
