@@ -336,6 +336,14 @@ class CudaStages:
                                                 cut[1].data_ptr(), _stream()))
         return cut
 
+    def topk_cutoff_sharded(self, plan: Plan, sample_sum: torch.Tensor, k: int, rank: int, world: int) -> torch.Tensor:
+        """Global cutoff from the rank-summed sample block (``collect_candidates``), index bound translated into this shard."""
+        cut = torch.empty((2, plan.Qpad), dtype=torch.int32, device=sample_sum.device)
+        with torch.cuda.device(sample_sum.device):
+            check(_lib.lib().cmh_tc_topk_cutoff_sharded(ctypes.byref(plan), sample_sum.data_ptr(), k, rank, world, cut[0].data_ptr(),
+                                                        cut[1].data_ptr(), _stream()))
+        return cut
+
     def topk_collect(self, plan: Plan, ops: Operands, cutoff: torch.Tensor, cap: int) -> Tuple[torch.Tensor, torch.Tensor]:
         dev = cutoff.device
         cand = torch.empty((plan.nchunks, plan.Qpad, cap), dtype=torch.int32, device=dev)
@@ -421,22 +429,41 @@ def candidate_path_ok(st, plan: Plan, n_local: int, k: int) -> bool:
             and (plan.nchunks + 1) * plan.bins * 4 <= 200 * 1024)   # cand_place_kernel keeps [nchunks][bins] counters per query
 
 
-def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None):
-    """sample histogram -> cutoff -> one tensor-core pass -> per-distance totals (+ fallback flag).  Returns (cap, cand, cnt, tot)."""
+def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None, allreduce_sum=None, idx_offset: int = 0, rank: int = 0,
+                       world: int = 1):
+    """sample histogram -> cutoff -> one tensor-core pass -> per-distance totals (+ fallback flag).
+    Returns (cap, cand, cnt, tot, meta).
+
+    ``allreduce_sum`` (sharded runs): a callable that sums an int32 tensor over the ranks in place.  The sample histograms are
+    then summed first, every rank derives the SAME global cutoff / index bound (so a rank keeps ~k/world candidates, not k), and
+    the "enough candidates" check is left to the caller, over all ranks (``meta`` = the summed sample block, row ``bins`` holds
+    [0] = sample items, [1] = gallery items of all ranks, [2 + r] = gallery index of rank r's first item)."""
+    dev = qp.device
     n_s = min(candidate_sample(plan.N), plan.N)
+    hist_s, plan_s = None, None
     if n_s > 0:
         plan_s = st.make_plan(plan.Q, n_s, plan.nbits, 0)
         hist_s = st.hist(plan_s, qp, None, gp[:n_s], None, ops=ops)
+    meta = None
+    if allreduce_sum is not None:
+        meta = torch.empty((plan.bins + 1, plan.Qpad), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().cmh_tc_topk_sample_block(ctypes.byref(plan_s) if plan_s is not None else None, _ptr(hist_s), plan.Qpad,
+                                                      plan.bins, plan.N, idx_offset, rank, world, meta.data_ptr(), _stream()))
+        allreduce_sum(meta)
+        cutoff = st.topk_cutoff_sharded(plan, meta, k, rank, world)
+    elif hist_s is not None:
         cutoff = st.topk_cutoff(plan_s, hist_s, plan.N, k)
     else:   # an empty shard has no candidates
-        cutoff = torch.full((2, plan.Qpad), -1, dtype=torch.int32, device=qp.device)
+        cutoff = torch.full((2, plan.Qpad), -1, dtype=torch.int32, device=dev)
     _mark(stages)
     cap = candidate_cap(plan, k)
     cand, cnt = st.topk_collect(plan, ops, cutoff, cap)
     _mark(stages)
-    tot = st.topk_count(plan, cap, cand, cnt, k)
+    tot = st.topk_count(plan, cap, cand, cnt, 0 if allreduce_sum is not None else k)
     _mark(stages)
-    return cap, cand, cnt, tot
+    return cap, cand, cnt, tot, meta
+
 
 MAP_STAGE_NAMES = ("expand", "hist_kernel", "scan", "rank_map_kernel", "map_finish")
 
@@ -509,7 +536,7 @@ def topk(qp, gp, nbits: int, k: int, idx_offset: int = 0, target_blocks: int = 0
     ops = st.operands(plan, qp, None, gp, None)
     _mark(stages)
     if exact is not True and candidate_path_ok(st, plan, N, k):
-        cap, cand, cnt, tot = collect_candidates(st, plan, ops, qp, gp, k, stages)
+        cap, cand, cnt, tot, _ = collect_candidates(st, plan, ops, qp, gp, k, stages)
         st.topk_place(plan, cap, cand, cnt, tot, 1, 0, k, idx_offset, keys)
         _mark(stages)
         if int(tot[plan.bins, 0].item()) == 0:     # verified: every cutoff was wide enough and no list overflowed
@@ -656,10 +683,18 @@ class ShardedEvaluator:
         _mark(stages)
         kw = {"ops": ops} if ops is not None else {}
         if (method != "allgather_merge" and exact is not True and ops is not None
-                and candidate_path_ok(st, plan, n_geom, k)):   # decided on the common geometry: same path on every rank
+                and candidate_path_ok(st, plan, n_geom, k) and self.world + 2 <= plan.Qpad):
+            # (decided on the common geometry: same path on every rank)
             # candidate path: local cutoffs guarantee >= min(k, n_local) LOCAL candidates, hence every item of the global top-k
-            cap, cand, cnt, tot = collect_candidates(st, plan, ops, qp, gp_local, k, stages)
-            tot_all = self._gather(tot)                            # [world, bins + 1, Qpad]: per-distance totals + fallback flag
+            cap, cand, cnt, tot, meta = collect_candidates(
+                st, plan, ops, qp, gp_local, k, stages, idx_offset=idx_offset, rank=self.rank, world=self.world,
+                allreduce_sum=lambda t: self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group))
+            tot_all = self._gather(tot)                            # [world, bins + 1, Qpad]: per-distance totals + overflow flag
+            # verified on every rank from the same gathered data: no list overflowed, and the candidates of ALL ranks together
+            # (a prefix of the global order) number at least min(k, gallery size) for every query
+            need = torch.clamp(meta[plan.bins, 1], max=k)
+            short = (tot_all[:, : plan.bins, :Q].sum(dim=(0, 1)) < need).any()
+            bad = short | (tot_all[:, plan.bins, 0].max() != 0)
             _mark(stages)
             symm = self._symmetric_keys(Q, k, qp.device) if method in ("auto", "nvls", "peer_stores") else None
             if method in ("nvls", "peer_stores") and symm is None:
@@ -696,7 +731,7 @@ class ShardedEvaluator:
                 keys = torch.full((Q, k), EMPTY_KEY, dtype=torch.int64, device=qp.device)
                 st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys)
                 self._exchange_keys(keys, method)
-            if int(tot_all[:, plan.bins, 0].max().item()) == 0:   # every rank verified its candidates (same answer on all ranks)
+            if not bool(bad.item()):   # same answer on every rank
                 return keys
         hist = st.hist(plan, qp, None, gp_local, None, **kw)
         if method in ("auto", "nvls", "peer_stores"):

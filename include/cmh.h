@@ -205,6 +205,7 @@ int cmh_tc_rank_map(const cmh_plan* plan, const cmh_tc_operands* ops, const uint
  *                        (0xFFFFFFFF = the list overflowed)
  *   cmh_tc_topk_count    totals[d][q] = #candidates at distance d ([bins][Qpad], what a rank exchanges); flags[0] |= 1 if a
  *                        list overflowed or a query has fewer than min(k, N) candidates -> caller must use the exact path
+ *                        (k = 0: only overflow is flagged — sharded runs check the candidate count over all ranks instead)
  *   cmh_tc_topk_place    keys[q][rank] for this shard's candidates with global stable rank < k; totals_all = the all-gathered
  *                        totals, rank r's [bins][Qpad] block starting at r * rank_stride elements.
  *                        Fused exchange (replaces the all-reduce of the [Q][k] buffer): with multicast_keys != NULL every key is
@@ -214,6 +215,16 @@ int cmh_tc_rank_map(const cmh_plan* plan, const cmh_tc_operands* ops, const uint
  *                        The caller owns the synchronisation (a barrier over the ranks before and after). */
 int cmh_tc_topk_cutoff(const cmh_plan* sample_plan, const uint32_t* hist_sample, int64_t n_local, int64_t k, int32_t* cutoff,
                        int32_t* ibound, void* stream);
+/* Sharded form of the cutoff: sample_sum = SUM over the ranks of (this rank's sample histogram totals [bins][Qpad] | row `bins`:
+ * [0] = its sample size, [1] = its shard size, [2 + r] = gallery index of its first item, written by rank r only), plain uint32
+ * [bins + 1][Qpad].  One GLOBAL cutoff and index bound per query, the bound translated into this rank's shard: every rank keeps
+ * ~k/world candidates and their union is a prefix of the global (distance, index) order. */
+/* This rank's contribution to that sum, built by ONE kernel from its sample histogram (hist_sample may be NULL for an empty
+ * shard): out[d][q] = sum over the sample chunks, out[bins][0..] = the header described above, everything else 0. */
+int cmh_tc_topk_sample_block(const cmh_plan* sample_plan, const uint32_t* hist_sample, int64_t Qpad, int bins, int64_t n_local,
+                             int64_t idx_offset, int rank, int world, uint32_t* out, void* stream);
+int cmh_tc_topk_cutoff_sharded(const cmh_plan* plan, const uint32_t* sample_sum, int64_t k, int rank, int world, int32_t* cutoff,
+                               int32_t* ibound, void* stream);
 int cmh_tc_topk_collect(const cmh_plan* plan, const cmh_tc_operands* ops, const int32_t* cutoff, const int32_t* ibound,
                         int cand_cap, uint32_t* cand, uint32_t* cand_count, void* stream);
 int cmh_tc_topk_count(const cmh_plan* plan, int cand_cap, const uint32_t* cand, const uint32_t* cand_count, int64_t k,

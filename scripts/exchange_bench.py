@@ -22,7 +22,7 @@ qp = R.pack_codes(synth.random_codes(Q, K, 1).to(dev))
 gp = R.pack_codes(synth.random_codes(N, K, 2)[lo:hi].contiguous().to(dev))
 plan = st.make_plan(Q, hi - lo, K, 0, n_geom)
 ops = st.operands(plan, qp, None, gp, None)
-cap, cand, cnt, tot = R.collect_candidates(st, plan, ops, qp, gp, k)
+cap, cand, cnt, tot, _ = R.collect_candidates(st, plan, ops, qp, gp, k)
 tot_all = ev._gather(tot)
 buf, hdl = ev._symmetric_keys(Q, k, dev)
 keys = torch.full((Q, k), -1, dtype=torch.int64, device=dev)

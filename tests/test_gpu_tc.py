@@ -162,7 +162,7 @@ def test_candidate_stages_sharded_equal_single(world):
     for lo, hi in bounds:
         plan = st.make_plan(Q, hi - lo, K, 0, n_geom)
         ops = st.operands(plan, qp, None, gp[lo:hi], None)
-        parts.append((plan, lo) + R.collect_candidates(st, plan, ops, qp, gp[lo:hi], k))
+        parts.append((plan, lo) + R.collect_candidates(st, plan, ops, qp, gp[lo:hi], k)[:4])
     tot_all = torch.stack([p[5] for p in parts]).contiguous()
     assert int(tot_all[:, parts[0][0].bins, 0].max()) == 0
     keys = torch.full((Q, k), R.EMPTY_KEY, dtype=torch.int64, device=DEV)
