@@ -199,7 +199,10 @@ class _Model(_RegistryMixin, torch.nn.Module):
         super().__init__()
         self.backbone = ClipBackbone(clip_state_dict, return_patches=False, device=device)
         self.hash = self.HASH(hash_state_dict, device)
-        self.output_dim = self.hash.nbits
+
+    @property
+    def output_dim(self):   # follows the head: a checkpoint with another code length may be loaded later
+        return self.hash.nbits
 
     def encode_image(self, image):          # models/DSPH/DSPH.py:37-42, models/DCMHT/DCMHT.py:37-42
         return self.hash.encode_img(self.backbone.encode_image(image))
@@ -255,6 +258,12 @@ class DSPH(_Model):
         if "hyp.proxies" in state_dict:                                       # models/DSPH/DSPH.py:33-35
             self.proxies = state_dict["hyp.proxies"].detach().float()
         return super().load_state_dict(state_dict, strict)
+
+    def state_dict(self, *a, **k):
+        out = super().state_dict(*a, **k)
+        if self.proxies is not None:                                          # keep a save / load round trip lossless
+            out["hyp.proxies"] = self.proxies
+        return out
 
     def object_function(self, img_hash, txt_hash, labels=None, indexs=None, **kwargs):
         """models/DSPH/DSPH.py:78-82 -> (loss, loss_dict); the VALUE of the HyP objective only, no gradient."""
@@ -413,7 +422,10 @@ class MITH(_RegistryMixin, torch.nn.Module):
         super().__init__()
         self.backbone = ClipBackbone(clip_state_dict, return_patches=True, device=device)
         self.hash = MithHashLayer(hash_state_dict, device, top_k_label)
-        self.output_dim = self.hash.nbits
+
+    @property
+    def output_dim(self):
+        return self.hash.nbits
 
     def _image(self, image, want_trans, packed):
         cls, tokens, _ = self.backbone.encode_image_raw(image, True, False)     # tokens [B, 50, E], row 0 = CLS
@@ -542,3 +554,18 @@ def get_code(model, data_loader, length: int, device=None, distributed: bool = F
     if distributed:
         merge_code_buffers(img_buf, txt_buf, group=group)
     return img_buf, txt_buf
+
+
+def register_into_reference(registry=None, names=("DSPH", "DCMHT", "MITH")):
+    """Make ``BaseTrainer.build_model`` (runners/base.py:98-102: ``registry.get_model_class(arch).from_config(...)``) return
+    these models for the given ``arch`` names.  The reference's ``registry.register_model`` decorator insists on a
+    ``BaseModel`` subclass and refuses names that are taken (common/register.py:75-91), so the mapping is overridden
+    directly.  Call after ``import models`` of the reference (its own classes register themselves at import time)."""
+    if registry is None:
+        from common.register import registry as _registry   # the reference's module
+
+        registry = _registry
+    table = {"DSPH": DSPH, "DCMHT": DCMHT, "MITH": MITH}
+    for n in names:
+        registry.mapping["model_name_mapping"][n] = table[n]
+    return registry
