@@ -132,6 +132,7 @@ PROTOTYPES = {
     "cmh_gemm_mma_lookahead": [_i32],
     "cmh_encoder_workspace_bytes": [_vp, _i64, _i32],
     "cmh_encode_image": [_vp, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp],
+    "cmh_encode_image_u8": [_vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _i64, _vp, _sz, _vp, _vp, _vp, _vp],
     "cmh_encode_text": [_vp, _vp, _vp, _i64, _i32, _vp, _sz, _vp, _vp, _vp, _vp, _vp],
     "cmh_layernorm": [_vp, _i64, _i32, _vp, _vp, ctypes.c_float, _vp, _i32, _vp],
     "cmh_attention_bf16": [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp],

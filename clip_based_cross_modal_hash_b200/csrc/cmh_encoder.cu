@@ -220,11 +220,12 @@ int64_t cmh_encoder_workspace_bytes(const cmh_tower* tower, int64_t batch, int32
     return cmh::carve(tower, batch, seq_len, nullptr).bytes;
 }
 
-int cmh_encode_image(const cmh_tower* t, const float* images, int64_t B, void* workspace, size_t workspace_bytes,
-                     float* cls_out, float* tokens_out, float* attn_out, void* stream) {
+static int encode_image_any(const cmh_tower* t, const float* images_f32, const uint8_t* images_u8, const float* mean, const float* stdv,
+                            int64_t B, void* workspace, size_t workspace_bytes, float* cls_out, float* tokens_out, float* attn_out,
+                            void* stream) {
     using namespace cmh;
     if (int rc = check_tower(t)) return rc;
-    CMH_REQUIRE(images && cls_out && B > 0, "encode_image: bad arguments");
+    CMH_REQUIRE((images_f32 || images_u8) && cls_out && B > 0, "encode_image: bad arguments");
     CMH_REQUIRE(t->patch > 0 && t->resolution % t->patch == 0 && t->w_patch && t->cls_emb && t->ln_pre_gain && t->ln_pre_bias,
                 "encode_image: not an image tower");
     const int g = t->resolution / t->patch, L = g * g + 1;
@@ -235,7 +236,11 @@ int cmh_encode_image(const cmh_tower* t, const float* images, int64_t B, void* w
     cudaStream_t st = as_stream(stream);
     const int64_t D = t->width, PK = int64_t(3) * t->patch * t->patch, MP = B * (L - 1);
     // conv1 as a GEMM over non-overlapping patches (model.py:235-238)
-    if (int rc = patchify(images, B, 3, t->resolution, t->patch, w.patches, st)) return rc;
+    if (images_u8) {
+        if (int rc = patchify_u8(images_u8, B, 3, t->resolution, t->patch, mean, stdv, w.patches, st)) return rc;
+    } else {
+        if (int rc = patchify(images_f32, B, 3, t->resolution, t->patch, w.patches, st)) return rc;
+    }
     if (int rc = gemm_bf16(w.patches, MP, PK, PK, t->w_patch, D, PK, nullptr, CMH_EPI_F32, w.emb, D, nullptr, 0, st)) return rc;
     // [CLS; patches] + positional embedding -> ln_pre (model.py:241-243)
     if (int rc = vit_assemble(w.emb, t->cls_emb, t->pos_emb, B, L, int(D), t->ln_pre_gain, t->ln_pre_bias, LN_EPS, w.x, st)) return rc;
@@ -244,6 +249,16 @@ int cmh_encode_image(const cmh_tower* t, const float* images, int64_t B, void* w
         if (int rc = attention_mean(w.probs, B, t->heads, L, 1, nullptr, attn_out, st)) return rc;
     }
     return project(t, w, B, L, nullptr, cls_out, tokens_out, st);
+}
+
+int cmh_encode_image(const cmh_tower* t, const float* images, int64_t B, void* workspace, size_t workspace_bytes,
+                     float* cls_out, float* tokens_out, float* attn_out, void* stream) {
+    return encode_image_any(t, images, nullptr, nullptr, nullptr, B, workspace, workspace_bytes, cls_out, tokens_out, attn_out, stream);
+}
+
+int cmh_encode_image_u8(const cmh_tower* t, const uint8_t* images, const float* mean_host, const float* std_host, int64_t B,
+                        void* workspace, size_t workspace_bytes, float* cls_out, float* tokens_out, float* attn_out, void* stream) {
+    return encode_image_any(t, nullptr, images, mean_host, std_host, B, workspace, workspace_bytes, cls_out, tokens_out, attn_out, stream);
 }
 
 int cmh_encode_text(const cmh_tower* t, const int64_t* text, const uint8_t* key_padding_mask, int64_t B, int32_t L,

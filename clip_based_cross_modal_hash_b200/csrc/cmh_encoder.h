@@ -20,6 +20,8 @@ int text_embed(const int64_t* text, const float* tok, const float* pos, int64_t 
 int text_eos(const int64_t* text, const uint8_t* pad, int64_t B, int L, int64_t eot_id, int32_t* eos, uint8_t* new_mask,
              cudaStream_t st);
 int patchify(const float* img, int64_t B, int C, int R, int P, void* out, cudaStream_t st);
+int patchify_u8(const uint8_t* img, int64_t B, int C, int R, int P, const float* mean_host, const float* std_host, void* out,
+                cudaStream_t st);
 
 // cmh_attention.cu
 int attention_bf16(const void* qkv, int64_t B, int L, int H, const uint8_t* pad, int causal, void* out, float* probs,

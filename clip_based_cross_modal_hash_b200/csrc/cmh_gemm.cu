@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 
 #include "cmh_common.cuh"
+#include "cmh_debug.h"
 #include "cmh_encoder.h"
 #include "cmh_tcgen05.cuh"
 

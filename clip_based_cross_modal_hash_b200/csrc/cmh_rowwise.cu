@@ -165,6 +165,37 @@ patchify_kernel(const float* __restrict__ img, int64_t B, int C, int R, int P, _
     }
 }
 
+// uint8 pixels straight from the dataloader (dataset/transformer_dataset.py:41-45: ToTensor's /255 and Normalize(mean, std) are
+// the only arithmetic left after Resize/CenterCrop): out = ((x / 255) - mean[c]) / std[c] as bf16 patches.  Thread = 16
+// consecutive pixels of one image row (16 B read, 32 B write).  A quarter of the fp32 bytes cross PCIe and HBM.
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t* __restrict__ img, int64_t B, int C, int R, int P, float3 scale, float3 shift,
+                   __nv_bfloat16* __restrict__ out) {
+    const int g = R / P, xv = R / 16;
+    const int64_t total = B * C * R * xv;
+    pdl_wait();
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int x16 = int(i % xv);
+        const int y = int((i / xv) % R);
+        const int c = int((i / (int64_t(xv) * R)) % C);
+        const int64_t b = i / (int64_t(xv) * R * C);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(img + ((b * C + c) * R + y) * R + x16 * 16));
+        const float sc = c == 0 ? scale.x : c == 1 ? scale.y : scale.z, sh = c == 0 ? shift.x : c == 1 ? shift.y : shift.z;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float p0 = fmaf(float(w[j] & 0xFFu), sc, sh), p1 = fmaf(float((w[j] >> 8) & 0xFFu), sc, sh);
+            const float p2 = fmaf(float((w[j] >> 16) & 0xFFu), sc, sh), p3 = fmaf(float(w[j] >> 24), sc, sh);
+            o[2 * j] = pack_bf16x2(p0, p1), o[2 * j + 1] = pack_bf16x2(p2, p3);
+        }
+        const int x = x16 * 16, px = x / P, kx = x % P, py = y / P, ky = y % P;
+        uint4* dst = reinterpret_cast<uint4*>(out + ((b * g + py) * g + px) * int64_t(C * P * P) + (c * P + ky) * P + kx);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
 template <int NV, bool OUT_F32>
 int launch_ln(const float* x, int64_t rows, int64_t row_mul, const int32_t* row_idx, const float* g, const float* b, float eps,
               void* out, cudaStream_t st) {
@@ -231,6 +262,21 @@ int patchify(const float* img, int64_t B, int C, int R, int P, void* out, cudaSt
     const int64_t cap = int64_t(sm_count_cached()) * 32;
     CMH_CUDA_TRY(launch_kernel(patchify_kernel, dim3(unsigned(blocks < cap ? blocks : cap)), dim3(256), 0, st, 1, img, B, C, R, P,
                                static_cast<__nv_bfloat16*>(out)));
+    return CMH_OK;
+}
+
+int patchify_u8(const uint8_t* img, int64_t B, int C, int R, int P, const float* mean, const float* std, void* out, cudaStream_t st) {
+    CMH_REQUIRE(C == 3 && R % P == 0 && P % 16 == 0 && R % 16 == 0, "patchify_u8: %d channels / resolution %d / patch %d unsupported", C, R, P);
+    CMH_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0, "patchify_u8: images must be 16-byte aligned");
+    CMH_REQUIRE(mean && std && std[0] != 0.f && std[1] != 0.f && std[2] != 0.f, "patchify_u8: mean / std");
+    // ((x / 255) - mean) / std  ==  x * scale + shift
+    const float3 scale = make_float3(1.f / (255.f * std[0]), 1.f / (255.f * std[1]), 1.f / (255.f * std[2]));
+    const float3 shift = make_float3(-mean[0] / std[0], -mean[1] / std[1], -mean[2] / std[2]);
+    const int64_t total = B * C * R * (R / 16);
+    const int64_t blocks = ceil_div(total, 256);
+    const int64_t cap = int64_t(sm_count_cached()) * 32;
+    CMH_CUDA_TRY(launch_kernel(patchify_u8_kernel, dim3(unsigned(blocks < cap ? blocks : cap)), dim3(256), 0, st, 1, img, B, C, R, P, scale,
+                               shift, static_cast<__nv_bfloat16*>(out)));
     return CMH_OK;
 }
 

@@ -118,6 +118,9 @@ class ClipBackbone(torch.nn.Module):
         super().__init__()
         self.return_patches = return_patches
         self.device_ = torch.device(device)
+        # Normalize(mean, std) of dataset/transformer_dataset.py:40,44 — applied on the GPU when images arrive as uint8
+        self.pixel_mean = (0.48145466, 0.4578275, 0.40821073)
+        self.pixel_std = (0.26862954, 0.26130258, 0.27577711)
         if self.device_.type != "cuda":
             raise _lib.CmhError("ClipBackbone needs a CUDA device (there is no CPU path)")
         skip = ("input_resolution", "context_length", "vocab_size")              # model.py:472-474
@@ -157,16 +160,20 @@ class ClipBackbone(torch.nn.Module):
         c = tw.c
         if image.dim() != 4 or image.shape[1] != 3 or image.shape[2] != c.resolution or image.shape[3] != c.resolution:
             raise ValueError("expected images [B, 3, %d, %d], got %s" % (c.resolution, c.resolution, tuple(image.shape)))
-        image = image.to(device=self.device_, dtype=torch.float32).contiguous()
+        u8 = image.dtype == torch.uint8   # raw pixels: /255 and Normalize(mean, std) happen on the GPU (self.pixel_mean / pixel_std)
+        image = image.to(device=self.device_, dtype=torch.uint8 if u8 else torch.float32).contiguous()
         B, L, E = image.shape[0], tw.seq_len, c.out_dim
         with torch.cuda.device(self.device_):
             ws = tw.workspace(B, L, self.device_)
             cls = torch.empty((B, E), dtype=torch.float32, device=self.device_)
             tokens = torch.empty((B, L, E), dtype=torch.float32, device=self.device_) if want_tokens else None
             attn = torch.empty((B, L - 1), dtype=torch.float32, device=self.device_) if want_attn else None
-            _lib.check(_lib.lib().cmh_encode_image(
-                ctypes.byref(c), image.data_ptr(), B, ws.data_ptr(), ws.numel(), cls.data_ptr(),
-                None if tokens is None else tokens.data_ptr(), None if attn is None else attn.data_ptr(), _stream()))
+            outs = (cls.data_ptr(), None if tokens is None else tokens.data_ptr(), None if attn is None else attn.data_ptr(), _stream())
+            if u8:
+                mean, std = (ctypes.c_float * 3)(*self.pixel_mean), (ctypes.c_float * 3)(*self.pixel_std)
+                _lib.check(_lib.lib().cmh_encode_image_u8(ctypes.byref(c), image.data_ptr(), mean, std, B, ws.data_ptr(), ws.numel(), *outs))
+            else:
+                _lib.check(_lib.lib().cmh_encode_image(ctypes.byref(c), image.data_ptr(), B, ws.data_ptr(), ws.numel(), *outs))
         return cls, tokens, attn
 
     def encode_image(self, image: torch.Tensor):

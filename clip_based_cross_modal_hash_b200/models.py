@@ -507,8 +507,10 @@ def get_code(model, data_loader, length: int, device=None, distributed: bool = F
         image, text, mask, _label, index = batch
         index = torch.as_tensor(index)
         n = image.shape[0]
-        if slots[j] is None or slots[j][0].shape[0] < n or slots[j][1].shape[1] != text.shape[1]:
-            slots[j] = [torch.empty((n,) + tuple(image.shape[1:]), dtype=torch.float32, device=dev),
+        want_dt = torch.uint8 if image.dtype == torch.uint8 else torch.float32
+        if slots[j] is None or slots[j][0].shape[0] < n or slots[j][1].shape[1] != text.shape[1] or slots[j][0].dtype != want_dt:
+            slots[j] = [torch.empty((n,) + tuple(image.shape[1:]), dtype=torch.uint8 if image.dtype == torch.uint8 else torch.float32,
+                                    device=dev),   # uint8 pixels stay uint8: normalised on the GPU (encoder.ClipBackbone)
                         torch.empty((n, text.shape[1]), dtype=torch.int64, device=dev),
                         torch.empty((n,), dtype=torch.int64, device=dev),
                         torch.empty((n, text.shape[1]), dtype=torch.bool, device=dev)]

@@ -142,6 +142,20 @@ def random_images(batch: int, seed: int, resolution: int = 224) -> torch.Tensor:
     return torch.randn((batch, 3, resolution, resolution), generator=g, dtype=torch.float32)
 
 
+def random_images_u8(batch: int, seed: int, resolution: int = 224) -> torch.Tensor:
+    """uint8 NCHW pixels: what the dataloader holds after Resize / CenterCrop, before ToTensor + Normalize
+    (dataset/transformer_dataset.py:41-45)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randint(0, 256, (batch, 3, resolution, resolution), generator=g, dtype=torch.uint8)
+
+
+def normalize_u8(images: torch.Tensor) -> torch.Tensor:
+    """ToTensor + Normalize of dataset/transformer_dataset.py:40,44 on uint8 NCHW -> the fp32 tensor the reference feeds."""
+    mean = torch.tensor((0.48145466, 0.4578275, 0.40821073)).view(1, 3, 1, 1)
+    std = torch.tensor((0.26862954, 0.26130258, 0.27577711)).view(1, 3, 1, 1)
+    return (images.to(torch.float32) / 255.0 - mean) / std
+
+
 def random_captions(batch: int, seed: int, max_words: int = 32, vocab: int = 49408):
     """int64 [B, max_words]: SOT, uniform word ids, EOT at position in [3, max_words-2], zero padding; and the
     key_padding_mask (text == 0) of dataset/transformer_dataset.py:82-86.  For a reduced vocabulary the SOT/EOT ids

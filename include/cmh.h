@@ -281,16 +281,7 @@ int cmh_euclid_sim_f32(const float* a, int64_t n, const float* b, int64_t m, int
 int cmh_gemm_bf16(const void* A, int64_t M, int64_t K, int64_t lda, const void* W, int64_t N, int64_t ldw,
                   const float* bias, int epilogue, void* out, int64_t ldo, const float* resid, int64_t ldr,
                   void* stream);
-/* Test / tuning hook: pin the tile width (128, 192, 256; 0 = automatic) and the CTA group (1 = one SM per tile,
- * 2 = tcgen05 cta_group::2 pairs on 256-row tiles; 0 = automatic) of every following cmh_gemm_bf16 call. */
-int cmh_gemm_force_tile(int bn, int cta_group);
-/* Debug timeline: when non-NULL, every following GEMM writes SM clock stamps into device_buffer[cta][64]
- * (0 entry, 1 set-up done, 2+4i.. per tile: accumulator wait / free / first operands landed / all MMAs issued,
- * 34+2i.. epilogue start / end of tile i, 63 exit). */
-int cmh_gemm_set_trace(long long* device_buffer);
-int cmh_gemm_mma_lookahead(int kblocks); /* tuning: k-blocks (4 MMAs each) the issuer may queue ahead, 1..8 (default 2) */
-int cmh_gemm_tail_slicing(int on);   /* debug: 0 disables the column slicing of the last partial wave's tiles */
-int cmh_gemm_force_units(int units); /* debug: cap the persistent grid at `units` CTAs (pairs for cta_group 2); 0 = all SMs */
+/* (tuning / trace hooks of the GEMM are not part of the product ABI: include/cmh_debug.h) */
 
 
 /* ---- E: CLIP encoders (models/CLIP/model.py) ---------------------------------------------------------------------
@@ -333,6 +324,11 @@ int64_t cmh_encoder_workspace_bytes(const cmh_tower* tower, int64_t batch, int32
  * column (model.py:265; NULL = skip).  The reference's seq_tokens [L-1][B][E] is tokens_out[:,1:].permute(1,0,2). */
 int cmh_encode_image(const cmh_tower* tower, const float* images, int64_t batch, void* workspace, size_t workspace_bytes,
                      float* cls_out, float* tokens_out, float* attn_out, void* stream);
+/* Same, from uint8 pixels [B][3][R][R] (what the dataloader holds after Resize / CenterCrop): ToTensor's /255 and
+ * Normalize(mean, std) of dataset/transformer_dataset.py:41-45 run on the GPU, fused into the patch gather — a quarter of the
+ * fp32 bytes cross PCIe and HBM.  mean_host / std_host = 3 HOST floats each (per channel). */
+int cmh_encode_image_u8(const cmh_tower* tower, const uint8_t* images, const float* mean_host, const float* std_host, int64_t batch,
+                        void* workspace, size_t workspace_bytes, float* cls_out, float* tokens_out, float* attn_out, void* stream);
 
 /* CLIP.encode_text (model.py:373-396).  text [B][L] int64 token ids; key_padding_mask [B][L] uint8 (1 = pad) or NULL.
  * Outputs: eos_out [B][out_dim] fp32 (required); tokens_out [B][L][out_dim] (NULL = skip);

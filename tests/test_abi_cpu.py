@@ -12,8 +12,8 @@ from clip_based_cross_modal_hash_b200 import _lib, calc_utils as cu, retrieval a
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_symbols():
-    text = open(os.path.join(ROOT, "include", "cmh.h")).read()
+def _header_symbols(header="cmh.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(cmh_[a-z0-9_]+)\s*\(", text)))
 
@@ -24,7 +24,11 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), "libcmh.so lacks %s" % n
-    assert sorted(_lib.PROTOTYPES) == names  # the ctypes table covers the header exactly
+    debug = _header_symbols("cmh_debug.h")      # tuning / trace hooks live in their own header, outside the product ABI
+    assert debug and not set(debug) & set(names)
+    for n in debug:
+        assert hasattr(lib, n), "libcmh.so lacks %s" % n
+    assert sorted(_lib.PROTOTYPES) == sorted(names + debug)  # the ctypes table covers both headers exactly
     assert lib.cmh_abi_version() == 1
 
 

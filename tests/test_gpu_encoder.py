@@ -296,3 +296,21 @@ def test_encoder_rejects_bad_arguments():
         ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
         _lib.check(_lib.lib().cmh_encode_image(ctypes.byref(c), torch.zeros(2, 3, 224, 224, device="cuda").data_ptr(), 2,
                                                ws.data_ptr(), ws.numel(), out.data_ptr(), None, None, st()))
+
+
+def test_uint8_images_are_normalised_on_the_gpu():
+    """uint8 pixels + GPU-side ToTensor/Normalize (dataset/transformer_dataset.py:41-45) == feeding the normalised fp32 tensor."""
+    sd = synth.clip_state_dict(synth.TINY, seed=3)
+    bb = encoder.ClipBackbone(sd)
+    u8 = synth.random_images_u8(6, seed=4)
+    want = bb.encode_image(synth.normalize_u8(u8))
+    got = bb.encode_image(u8)
+    # same bf16 patches up to the last fp32 ulp of the affine map before rounding: features agree far inside the bf16 tolerance
+    assert (got - want).norm() / want.norm() < 2e-3
+    oracle = port.encode_image(sd, synth.normalize_u8(u8))
+    check_features(got.cpu(), oracle)
+    model = models.DSPH(sd, synth.dsph_head_state_dict(synth.TINY["embed_dim"], 32, seed=9))
+    text, pad = synth.random_captions(6, seed=40, vocab=synth.TINY["vocab_size"])
+    loader = [(u8.pin_memory(), text.pin_memory(), pad, None, torch.arange(6))]
+    codes_u8, _ = models.get_code(model, loader, 6)
+    assert torch.equal(codes_u8, model.encode_image_packed(u8))
