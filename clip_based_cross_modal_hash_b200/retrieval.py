@@ -416,9 +416,9 @@ def candidate_sample(n_local: int) -> int:
 
 
 def candidate_cap(plan: Plan, k: int) -> int:
-    """Capacity of one (chunk, query) candidate list: 8x the mean of a k-candidate query, power of two in [64, 1024]."""
-    want = max(64, 8 * k // max(plan.nchunks, 1))
-    cap = 64
+    """Capacity of one (chunk, query) candidate list: 8x the mean of a k-candidate query, power of two in [128, 1024]."""
+    want = max(128, 8 * k // max(plan.nchunks, 1))
+    cap = 128
     while cap < want and cap < 1024:
         cap *= 2
     return cap
