@@ -335,9 +335,12 @@ def hamming_topk(qB, rB, k: int, out=None):
     nbits = rB.shape[1]
     with torch.cuda.device(dev):
         bad = R.new_bad_counter(dev)
-        qp = R.pack_codes(_to_dev(qB.detach(), dev), bad)
-        gp = R.pack_codes(_to_dev(rB.detach(), dev), bad)
-        keys = R.topk(qp, gp, nbits, k)
+        if not qB.is_cuda and not rB.is_cuda and qB.dtype == torch.float32 and rB.dtype == torch.float32 and nbits <= 128:
+            keys = R.topk_from_host(qB.detach(), rB.detach(), k, dev, bad=bad)    # host inputs: transfer overlapped with compute
+        else:
+            qp = R.pack_codes(_to_dev(qB.detach(), dev), bad)
+            gp = R.pack_codes(_to_dev(rB.detach(), dev), bad)
+            keys = R.topk(qp, gp, nbits, k)
         dist, idx = R.split_keys(keys, dist_dtype=torch.float32)
         return _topk_result(dist, idx, bad, qB, out)
 

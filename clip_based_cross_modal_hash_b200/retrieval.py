@@ -70,9 +70,9 @@ def new_bad_counter(device) -> torch.Tensor:
     return torch.zeros(1, dtype=torch.int64, device=device)
 
 
-def pack_codes(codes: torch.Tensor, bad: Optional[torch.Tensor] = None) -> torch.Tensor:
+def pack_codes(codes: torch.Tensor, bad: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[n, K] fp32 (+-1) CUDA -> [n, W] int32 (uint32 bit patterns).  ``bad`` (int64[1], device) counts
-    elements that are not exactly +-1 (it is added to, not reset)."""
+    elements that are not exactly +-1 (it is added to, not reset).  ``out``: optional contiguous [n, W] int32 destination."""
     _need_cuda(codes, bad)
     if codes.dim() != 2:
         raise CmhError("codes must be [n, K]")
@@ -81,7 +81,10 @@ def pack_codes(codes: torch.Tensor, bad: Optional[torch.Tensor] = None) -> torch
     if codes.stride(1) != 1:
         codes = codes.contiguous()
     n, nbits = codes.shape
-    out = torch.empty((n, code_words(nbits)), dtype=torch.int32, device=codes.device)
+    if out is None:
+        out = torch.empty((n, code_words(nbits)), dtype=torch.int32, device=codes.device)
+    elif out.shape != (n, code_words(nbits)) or out.dtype != torch.int32 or not out.is_contiguous():
+        raise CmhError("out must be a contiguous int32 [n, W] tensor")
     with torch.cuda.device(codes.device):
         check(_lib.lib().cmh_pack_codes_f32(codes.data_ptr(), n, nbits, codes.stride(0) if n > 1 else nbits,
                                             out.data_ptr(), _ptr(bad), _stream()))
@@ -169,11 +172,12 @@ class Operands:
                             q_codes.shape[1], 0 if q_labels is None else q_labels.shape[1])
 
 
-def _expand(packed: torch.Tensor, rows: int, ncols: int, kind: int) -> torch.Tensor:
+def _expand(packed: torch.Tensor, rows: int, ncols: int, kind: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     nb = _lib.lib().cmh_tc_operand_bytes(ncols)
     if nb < 0:
         raise CmhError("operand width %d not supported" % ncols)
-    out = torch.empty((rows, nb), dtype=torch.int8, device=packed.device)
+    if out is None:
+        out = torch.empty((rows, nb), dtype=torch.int8, device=packed.device)
     check(_lib.lib().cmh_tc_expand(packed.data_ptr(), packed.shape[0], rows, packed.shape[1], ncols, kind, out.data_ptr(), _stream()))
     return out
 
@@ -344,13 +348,19 @@ class CudaStages:
                                                         cut[1].data_ptr(), _stream()))
         return cut
 
-    def topk_collect(self, plan: Plan, ops: Operands, cutoff: torch.Tensor, cap: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    def topk_collect(self, plan: Plan, ops: Operands, cutoff: torch.Tensor, cap: int, out=None, chunks: Optional[Tuple[int, int]] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``chunks=(c0, c1)`` collects only chunks [c0, c1) into the ``out=(cand, cnt)`` buffers of an earlier call (slab pipeline)."""
         dev = cutoff.device
-        cand = torch.empty((plan.nchunks, plan.Qpad, cap), dtype=torch.int32, device=dev)
-        cnt = torch.empty((plan.nchunks, plan.Qpad), dtype=torch.int32, device=dev)
+        if out is None:
+            cand = torch.empty((plan.nchunks, plan.Qpad, cap), dtype=torch.int32, device=dev)
+            cnt = torch.empty((plan.nchunks, plan.Qpad), dtype=torch.int32, device=dev)
+        else:
+            cand, cnt = out
+        c0, c1 = chunks if chunks is not None else (0, 0)
         with torch.cuda.device(dev):
             check(_lib.lib().cmh_tc_topk_collect(ctypes.byref(plan), ctypes.byref(ops.c), cutoff[0].data_ptr(), cutoff[1].data_ptr(),
-                                                 cap, cand.data_ptr(), cnt.data_ptr(), _stream()))
+                                                 cap, cand.data_ptr(), cnt.data_ptr(), c0, c1, _stream()))
         return cand, cnt
 
     def topk_count(self, plan: Plan, cap: int, cand: torch.Tensor, cnt: torch.Tensor, k: int) -> torch.Tensor:
@@ -551,6 +561,71 @@ def topk(qp, gp, nbits: int, k: int, idx_offset: int = 0, target_blocks: int = 0
     st.rank_topk(plan, qp, gp, sc, k, idx_offset, keys=keys, ops=ops)
     _mark(stages)
     return keys
+
+
+def topk_from_host(q_host: torch.Tensor, g_host: torch.Tensor, k: int, device, slabs: int = 6, bad: Optional[torch.Tensor] = None
+                   ) -> torch.Tensor:
+    """``topk`` for +-1 fp32 code matrices that still live in (ideally pinned) HOST memory: the gallery crosses PCIe in slabs of
+    whole chunks on a copy stream while the slabs that have landed are packed, expanded and COLLECTED on the compute stream, so
+    the transfer (the longer of the two by far: 256 MB for 1 M x 64 bit) hides the compute instead of preceding it.
+    Same keys as ``topk(pack_codes(q), pack_codes(g), ...)``; falls back to that call when the candidate path does not apply."""
+    dev = torch.device(device)
+    Q, nbits = q_host.shape
+    N = g_host.shape[0]
+    k = _check_k(k)
+    st = CudaStages()
+    plan = st.make_plan(Q, N, nbits, 0)
+    main = torch.cuda.current_stream(dev)
+    if bad is None:
+        bad = new_bad_counter(dev)
+    with torch.cuda.device(dev):
+        qp = pack_codes(q_host.to(dev, non_blocking=True), bad)
+        per_slab = -(-plan.nchunks // max(1, slabs))
+        n_s = min(candidate_sample(N), N)
+        # the first slab must hold the sample prefix
+        first = max(per_slab, -(-n_s // plan.chunk_items))
+        if not candidate_path_ok(st, plan, N, k) or first >= plan.nchunks or g_host.dtype != torch.float32 or g_host.stride(1) != 1:
+            return topk(qp, pack_codes(g_host.to(dev, non_blocking=True), bad), nbits, k)
+        gp = torch.empty((N, code_words(nbits)), dtype=torch.int32, device=dev)
+        g_ops = torch.empty((N, _lib.lib().cmh_tc_operand_bytes(nbits)), dtype=torch.int8, device=dev)
+        ops = Operands(_expand(qp, plan.Qpad, nbits, 0), None, g_ops, None)
+        bounds, c = [], 0
+        while c < plan.nchunks:
+            c1 = min(plan.nchunks, c + (first if c == 0 else per_slab))
+            bounds.append((c, c1))
+            c = c1
+        copy = torch.cuda.Stream(dev)
+        max_items = max((c1 - c0) for c0, c1 in bounds) * plan.chunk_items
+        stage = [torch.empty((max_items, nbits), dtype=torch.float32, device=dev) for _ in range(2)]
+        free = [None, None]
+        cap = candidate_cap(plan, k)
+        cand = cnt = cutoff = None
+        for j, (c0, c1) in enumerate(bounds):
+            lo, hi = c0 * plan.chunk_items, min(N, c1 * plan.chunk_items)
+            buf = stage[j & 1][: hi - lo]
+            if free[j & 1] is not None:
+                copy.wait_event(free[j & 1])
+            else:
+                copy.wait_stream(main)               # the staging buffers were allocated on the compute stream
+            with torch.cuda.stream(copy):
+                buf.copy_(g_host[lo:hi], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(copy)
+            main.wait_event(landed)
+            pack_codes(buf, bad, out=gp[lo:hi])
+            free[j & 1] = torch.cuda.Event()
+            free[j & 1].record(main)
+            check(_lib.lib().cmh_tc_expand(gp[lo:hi].data_ptr(), hi - lo, hi - lo, gp.shape[1], nbits, 0, g_ops[lo:hi].data_ptr(), _stream()))
+            if j == 0:   # the sample prefix is on the device: cutoffs
+                plan_s = st.make_plan(Q, n_s, nbits, 0)
+                cutoff = st.topk_cutoff(plan_s, st.hist(plan_s, qp, None, gp[:n_s], None, ops=ops), N, k)
+            cand, cnt = st.topk_collect(plan, ops, cutoff, cap, out=None if cand is None else (cand, cnt), chunks=(c0, c1))
+        tot = st.topk_count(plan, cap, cand, cnt, k)
+        keys = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        st.topk_place(plan, cap, cand, cnt, tot, 1, 0, k, 0, keys)
+        if int(tot[plan.bins, 0].item()) == 0:
+            return keys
+        return topk(qp, gp, nbits, k, exact=True)     # verified-failed: exact two-pass path on the codes that are now resident
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -225,8 +225,10 @@ int cmh_tc_topk_sample_block(const cmh_plan* sample_plan, const uint32_t* hist_s
                              int64_t idx_offset, int rank, int world, uint32_t* out, void* stream);
 int cmh_tc_topk_cutoff_sharded(const cmh_plan* plan, const uint32_t* sample_sum, int64_t k, int rank, int world, int32_t* cutoff,
                                int32_t* ibound, void* stream);
+/* chunk_begin / chunk_end: the launch covers chunks [chunk_begin, chunk_end) of the plan (chunk_end <= 0: all).  Lets a caller
+ * whose gallery is still arriving from the host collect slab by slab while the next slab is in flight (calc_utils.hamming_topk). */
 int cmh_tc_topk_collect(const cmh_plan* plan, const cmh_tc_operands* ops, const int32_t* cutoff, const int32_t* ibound,
-                        int cand_cap, uint32_t* cand, uint32_t* cand_count, void* stream);
+                        int cand_cap, uint32_t* cand, uint32_t* cand_count, int chunk_begin, int chunk_end, void* stream);
 int cmh_tc_topk_count(const cmh_plan* plan, int cand_cap, const uint32_t* cand, const uint32_t* cand_count, int64_t k,
                       uint32_t* totals, int32_t* flags, void* stream);
 int cmh_tc_topk_place(const cmh_plan* plan, int cand_cap, const uint32_t* cand, const uint32_t* cand_count,

@@ -172,3 +172,23 @@ def test_candidate_stages_sharded_equal_single(world):
         assert int(((mine != R.EMPTY_KEY) & (keys != R.EMPTY_KEY)).sum()) == 0   # every slot has exactly one owner
         keys = torch.maximum(keys, mine)
     assert torch.equal(keys, want)
+
+
+def test_topk_from_host_slab_pipeline_equals_resident_path():
+    """host +-1 fp32 codes streamed in slabs (H2D overlapped with pack / expand / collect) == codes resident on the GPU."""
+    from clip_based_cross_modal_hash_b200 import calc_utils as cu
+
+    Q, N, K, k = 500, 330_001, 64, 300
+    qB, rB = synth.random_codes(Q, K, 71), synth.random_codes(N, K, 72)
+    want = R.topk(R.pack_codes(qB.to(DEV)), R.pack_codes(rB.to(DEV)), K, k, exact=True)
+    got = R.topk_from_host(qB.pin_memory(), rB.pin_memory(), k, DEV)
+    assert torch.equal(got, want)
+    got2 = R.topk_from_host(qB, rB, k, DEV, slabs=3)          # pageable memory, other slab count
+    assert torch.equal(got2, want)
+    dist, idx = cu.hamming_topk(qB, rB, k)                     # the public call takes this path for host inputs
+    wd, wi = R.split_keys(want)
+    assert torch.equal(idx, wi.cpu()) and torch.equal(dist, wd.cpu().float())
+    bad = rB.clone()
+    bad[N - 5, 3] = 0.0                                        # a non +-1 element in the LAST slab is still reported
+    with pytest.raises(ValueError):
+        cu.hamming_topk(qB, bad, k)
