@@ -140,6 +140,11 @@ PROTOTYPES = {
     "cmh_head_dsph": [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "cmh_head_dcmht": [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp],
     "cmh_hyp_loss_f32": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, ctypes.c_float, ctypes.c_float, _vp, _sz, _vp, _vp],
+    "cmh_hyp_loss_grad_f32": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, ctypes.c_float, ctypes.c_float, _vp, _sz, _vp, _vp, _vp, _vp, _vp],
+    "cmh_linear_tanh_backward_f32": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "cmh_opt_chunk_elems": [],
+    "cmh_bert_adam_step": [_vp, _i32, _vp, _vp, _i32, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp],
+    "cmh_sgd_momentum_step": [_vp, _i32, _vp, _vp, _i32, ctypes.c_float, _i32, _vp],
     "cmh_head_mith_workspace_bytes": [_vp, _i64, _i32],
     "cmh_head_mith": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp],
 }

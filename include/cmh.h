@@ -427,6 +427,43 @@ int cmh_head_mith(const cmh_mith_head* head, const float* cls, const float* toke
                   size_t workspace_bytes, float* res_cls, float* cls_hash, float* tokens_hash, float* trans_tokens,
                   uint32_t* packed, void* stream);
 
+/* ---- TR: the tail of the DSPH training step (BASELINE config C5; runners/DSPH/runner.py:104-127) -------------------------
+ * What a step needs besides the encoder's forward/backward: the objective's gradient, the hash head's backward and the
+ * optimiser.  The backward pass through the CLIP towers is not part of this library.
+ *
+ * cmh_hyp_loss_grad_f32: HyP.forward + what loss.backward() leaves in x.grad, y.grad and hyp.proxies.grad
+ *   (models/DSPH/loss/HyP.py:18-69).  Arguments as cmh_hyp_loss_f32 plus dx, dy [B][nbits] and dproxies [ncls][nbits] (fp32, written).
+ * cmh_linear_tanh_backward_f32: backward of y = tanh(feat . W^T + b) (models/DSPH/hash/hash.py:6-15, dropout off):
+ *   dW [nbits][in_dim], db [nbits] (may be NULL), dfeat [rows][in_dim] (may be NULL); dz_scratch = fp32 [rows][nbits]. */
+int cmh_hyp_loss_grad_f32(const float* x, const float* y, const uint32_t* labels_packed, const float* proxies, int64_t batch, int nbits,
+                          int ncls, float threshold, float alpha, void* workspace, size_t workspace_bytes, float* loss_out, float* dx,
+                          float* dy, float* dproxies, void* stream);
+int cmh_linear_tanh_backward_f32(const float* feat, const float* y, const float* dy, const float* W, int64_t rows, int in_dim, int nbits,
+                                 float* dz_scratch, float* dW, float* db, float* dfeat, void* stream);
+
+/* Fused multi-tensor optimiser steps.  One launch updates EVERY tensor (the reference loops over tensors in Python,
+ * models/common/optimizer.py:118-163: ~300 tensors x ~10 small kernels per step).  The caller keeps a DEVICE array of
+ * cmh_opt_tensor (lr = the scheduled learning rate of the tensor's group for this step) and a block table: block b works on
+ * elements [block_chunk[b] * cmh_opt_chunk_elems(), ...) of tensor block_tensor[b].
+ * cmh_bert_adam_step == BertAdam.step (:130-165): per-tensor clip_grad_norm_ (in place), next_m / next_v, update = m / (sqrt(v) + e)
+ *   + weight_decay * p, p -= lr * update; no bias correction.  sumsq_dev = fp32 [ntensors] scratch.
+ * cmh_sgd_momentum_step == torch.optim.SGD(momentum, weight_decay) as built for the HyP proxies (runners/DSPH/runner.py:86-89);
+ *   `m` is the momentum buffer, first_step != 0 initialises it with the gradient like torch does. */
+typedef struct cmh_opt_tensor {
+    float* param;
+    float* grad;
+    float* m;
+    float* v;
+    int64_t n;
+    float lr;
+    float weight_decay;
+} cmh_opt_tensor;
+int cmh_opt_chunk_elems(void);
+int cmh_bert_adam_step(const cmh_opt_tensor* tensors_dev, int ntensors, const int32_t* block_tensor_dev, const int32_t* block_chunk_dev,
+                       int nblocks, float* sumsq_dev, float b1, float b2, float e, float max_grad_norm, void* stream);
+int cmh_sgd_momentum_step(const cmh_opt_tensor* tensors_dev, int ntensors, const int32_t* block_tensor_dev, const int32_t* block_chunk_dev,
+                          int nblocks, float momentum, int first_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
