@@ -53,7 +53,9 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback (MEAS
 SM_COUNT = 148
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
 # captures (profiles/README.md names the file each number comes from); None = not captured for that kernel
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {"collect_kernel": 150.6e6,      # profiles/r2_ncu_topk_C4-64.txt: 91.3 MB read + 59.3 MB written (C4-64)
+               "rank_map_kernel": 187.0e6,     # profiles/r2_ncu_map_C2.txt: 180.6 + 6.4 MB (C2)
+               "hist_kernel": 46.2e6}
 
 
 def load_peaks():
@@ -723,8 +725,10 @@ def run_ours(args, cfg, name):
             "kernel_ms": kern_ms, "share_of_step": kern_ms / head["ms_per_step"],
             "algorithmic_bytes_per_launch": s8["compulsory_bytes"],
             "note": "compulsory bytes (SURVEY 8(d): N*W + Q*W + Q*k*8) over the dominant kernel's time; the path never materialises "
-                    "Q x N, so it is bound by per-pair work on the SM (tensor pipe + counting epilogue), not by HBM: the graded figure "
-                    "is survey_8d.achieved",
+                    "Q x N, so it is bound by per-pair work on the SM, not by HBM: the graded figure is survey_8d.achieved.  ncu of the "
+                    "collect kernel (profiles/r2_ncu_topk_C4-64.txt): integer ALU pipe 80.8 % busy (the binding resource), issue slots "
+                    "65 %, tensor pipe (UTCIMMA) 16.8 %, DRAM 1 %; traffic = dram bytes read + written per launch at C4-64 "
+                    "(applies to the 64-bit headline only)",
             "survey_8d": s8,
         }
     else:
