@@ -1,4 +1,4 @@
-"""The tail of the DSPH training step on the GPU (BASELINE.json config C5; DESIGN.md §11): fused optimisers, the HyP
+"""The tail of the DSPH training step on the GPU (BASELINE.json config C5; DESIGN.md §10): fused optimisers, the HyP
 objective's gradient, the tanh(Linear) hash head's backward, and a frozen-backbone training step built from them.
 
     reference                                               here
