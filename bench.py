@@ -781,7 +781,7 @@ def main():
     ap.add_argument("--workload", default="C4-64", choices=sorted(synth.CONFIGS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="top-k only: strong = the workload's gallery split over the GPUs (default), weak = one full gallery per GPU")
-    ap.add_argument("--topk-exchange", default="auto", choices=["auto", "nvls", "peer_stores", "rank_scatter", "allgather_merge"])
+    ap.add_argument("--topk-exchange", default="auto", choices=["auto", "nvls", "nvls_reduce", "peer_stores", "rank_scatter", "allgather_merge"])
     ap.add_argument("--no-encode", action="store_true", help="skip the CLIP encode section of the line")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 16/32/128-bit sweep")
     ap.add_argument("--no-c2", action="store_true", help="skip the C2 mAP object")

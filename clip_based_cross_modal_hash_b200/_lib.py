@@ -121,6 +121,8 @@ PROTOTYPES = {
     "cmh_tc_topk_count": [_PP, _i32, _vp, _vp, _i64, _vp, _vp, _vp],
     "cmh_tc_topk_place": [_PP, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _vp],
     "cmh_nvls_allreduce_max_s64": [_vp, _i64, _i32, _i32, _vp],
+    "cmh_nvls_push_owned_s64": [_vp, _vp, _i64, _vp],
+    "cmh_nvls_broadcast": [_vp, _vp, _i64, _vp],
     "cmh_label_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],
     "cmh_cosine_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],
     "cmh_euclid_sim_f32": [_vp, _i64, _vp, _i64, _i32, _vp, _vp],

@@ -31,10 +31,55 @@ __global__ void __launch_bounds__(256) nvls_allreduce_max_kernel(long long* mc, 
     }
 }
 
+// Broadcast of a rank's own block into the same place of EVERY rank's symmetric buffer: plain 16-byte loads of the local source,
+// 16-byte multicast stores (fire and forget — no round trip through the switch).  Used for the small exchanges of the sharded
+// top-k (sample histograms, per-distance totals: 2.7 MB per rank), where an NCCL collective is launch- and latency-bound.
+__global__ void __launch_bounds__(256) nvls_broadcast_kernel(const float4* __restrict__ src, float4* mc_dst, int64_t n16) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += int64_t(gridDim.x) * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+    }
+}
+
+// Result exchange without a reduction: every slot of the [Q][k] key buffer has exactly one owner, so each rank pushes the slots
+// it owns (everything that is not EMPTY in its local placement buffer) to all ranks with multicast stores; coalesced over slots.
+__global__ void __launch_bounds__(256) nvls_push_owned_kernel(const long long* __restrict__ local, long long* mc, int64_t n) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const long long v = __ldg(local + i);
+        if (v != -1) asm volatile("multimem.st.relaxed.sys.global.s64 [%0], %1;" ::"l"(mc + i), "l"(v) : "memory");
+    }
+}
+
 }  // namespace
 }  // namespace cmh
 
 using namespace cmh;
+
+extern "C" int cmh_nvls_broadcast(const void* src, void* multicast_dst, int64_t bytes, void* stream) {
+    CMH_REQUIRE(src && multicast_dst && bytes >= 0 && bytes % 16 == 0, "nvls_broadcast: bytes must be a multiple of 16");
+    CMH_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(multicast_dst)) & 15) == 0, "nvls_broadcast: 16-byte alignment");
+    if (bytes == 0) return CMH_OK;
+    const int64_t n16 = bytes / 16;
+    int64_t blocks = ceil_div(n16, 256);
+    const int64_t cap = int64_t(sm_count_cached()) * 4;
+    if (blocks > cap) blocks = cap;
+    nvls_broadcast_kernel<<<unsigned(blocks), 256, 0, as_stream(stream)>>>(static_cast<const float4*>(src), static_cast<float4*>(multicast_dst), n16);
+    CMH_LAUNCH_CHECK("nvls_broadcast_kernel");
+    return CMH_OK;
+}
+
+extern "C" int cmh_nvls_push_owned_s64(const void* local_keys, void* multicast_keys, int64_t count, void* stream) {
+    CMH_REQUIRE(local_keys && multicast_keys && count >= 0, "nvls_push_owned: bad arguments");
+    if (count == 0) return CMH_OK;
+    int64_t blocks = ceil_div(count, 256 * 4);
+    const int64_t cap = int64_t(sm_count_cached()) * 8;
+    if (blocks > cap) blocks = cap;
+    nvls_push_owned_kernel<<<unsigned(blocks), 256, 0, as_stream(stream)>>>(static_cast<const long long*>(local_keys),
+                                                                            static_cast<long long*>(multicast_keys), count);
+    CMH_LAUNCH_CHECK("nvls_push_owned_kernel");
+    return CMH_OK;
+}
 
 extern "C" int cmh_nvls_allreduce_max_s64(void* multicast_ptr, int64_t count, int rank, int world, void* stream) {
     CMH_REQUIRE(multicast_ptr && count >= 0 && world >= 1 && rank >= 0 && rank < world, "nvls_allreduce_max: bad arguments");

@@ -341,7 +341,10 @@ class CudaStages:
         return cut
 
     def topk_cutoff_sharded(self, plan: Plan, sample_sum: torch.Tensor, k: int, rank: int, world: int) -> torch.Tensor:
-        """Global cutoff from the rank-summed sample block (``collect_candidates``), index bound translated into this shard."""
+        """Global cutoff from the gathered sample blocks ``[world, bins + 1, Qpad]`` of all ranks (``collect_candidates``), index
+        bound translated into this shard."""
+        if tuple(sample_sum.shape) != (world, plan.bins + 1, plan.Qpad) or not sample_sum.is_contiguous():
+            raise CmhError("topk_cutoff_sharded: sample blocks must be a contiguous [world, bins + 1, Qpad] tensor")
         cut = torch.empty((2, plan.Qpad), dtype=torch.int32, device=sample_sum.device)
         with torch.cuda.device(sample_sum.device):
             check(_lib.lib().cmh_tc_topk_cutoff_sharded(ctypes.byref(plan), sample_sum.data_ptr(), k, rank, world, cut[0].data_ptr(),
@@ -439,15 +442,15 @@ def candidate_path_ok(st, plan: Plan, n_local: int, k: int) -> bool:
             and (plan.nchunks + 1) * plan.bins * 4 <= 200 * 1024)   # cand_place_kernel keeps [nchunks][bins] counters per query
 
 
-def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None, allreduce_sum=None, idx_offset: int = 0, rank: int = 0,
+def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None, gather=None, idx_offset: int = 0, rank: int = 0,
                        world: int = 1):
     """sample histogram -> cutoff -> one tensor-core pass -> per-distance totals (+ fallback flag).
     Returns (cap, cand, cnt, tot, meta).
 
-    ``allreduce_sum`` (sharded runs): a callable that sums an int32 tensor over the ranks in place.  The sample histograms are
-    then summed first, every rank derives the SAME global cutoff / index bound (so a rank keeps ~k/world candidates, not k), and
-    the "enough candidates" check is left to the caller, over all ranks (``meta`` = the summed sample block, row ``bins`` holds
-    [0] = sample items, [1] = gallery items of all ranks, [2 + r] = gallery index of rank r's first item)."""
+    ``gather`` (sharded runs): a callable that all-gathers an int32 ``[rows, Qpad]`` tensor into ``[world, rows, Qpad]``.  The
+    sample blocks are exchanged first, every rank derives the SAME global cutoff / index bound (so a rank keeps ~k/world
+    candidates, not k), and the "enough candidates" check is left to the caller, over all ranks (``meta`` = the gathered sample
+    blocks; rank r's row ``bins`` holds [0] = its sample items, [1] = its gallery items, [2 + r] = its first gallery index)."""
     dev = qp.device
     n_s = min(candidate_sample(plan.N), plan.N)
     hist_s, plan_s = None, None
@@ -455,12 +458,12 @@ def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None, allredu
         plan_s = st.make_plan(plan.Q, n_s, plan.nbits, 0)
         hist_s = st.hist(plan_s, qp, None, gp[:n_s], None, ops=ops)
     meta = None
-    if allreduce_sum is not None:
+    if gather is not None:
         meta = torch.empty((plan.bins + 1, plan.Qpad), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             check(_lib.lib().cmh_tc_topk_sample_block(ctypes.byref(plan_s) if plan_s is not None else None, _ptr(hist_s), plan.Qpad,
                                                       plan.bins, plan.N, idx_offset, rank, world, meta.data_ptr(), _stream()))
-        allreduce_sum(meta)
+        meta = gather(meta)
         cutoff = st.topk_cutoff_sharded(plan, meta, k, rank, world)
     elif hist_s is not None:
         cutoff = st.topk_cutoff(plan_s, hist_s, plan.N, k)
@@ -470,7 +473,7 @@ def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None, allredu
     cap = candidate_cap(plan, k)
     cand, cnt = st.topk_collect(plan, ops, cutoff, cap)
     _mark(stages)
-    tot = st.topk_count(plan, cap, cand, cnt, 0 if allreduce_sum is not None else k)
+    tot = st.topk_count(plan, cap, cand, cnt, 0 if gather is not None else k)
     _mark(stages)
     return cap, cand, cnt, tot, meta
 
@@ -656,22 +659,22 @@ class ShardedEvaluator:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.stages = stages if stages is not None else CudaStages()
-        self._symm = {}          # (Q, k, device) -> (tensor, handle) symmetric [Q, k] key buffers of the fused exchange
+        self._symm = {}          # (tag, shape, dtype, device) -> (tensor, handle): symmetric buffers of the fused exchanges
         self._symm_broken = None  # reason symmetric memory is unusable in this process group, once known
 
-    # ---- fused exchange: every rank's [Q, k] key buffer is mapped into every other rank (NVLink / NVSwitch) ----
-    def _symmetric_keys(self, Q: int, k: int, device):
-        """Symmetric-memory [Q, k] int64 buffer + its rendezvous handle (cached per shape); None when this build / box / group
-        cannot map peer memory (then the all-reduce exchange is used).  Collective: every rank must call it with the same shape."""
+    # ---- fused exchange: buffers of every rank mapped into every other rank and at one multicast address (NVLink / NVSwitch) ----
+    def _symmetric(self, tag: str, shape, dtype, device):
+        """Symmetric-memory buffer + its rendezvous handle (cached per tag and shape); None when this build / box / group cannot
+        map peer memory (then the NCCL exchanges are used).  Collective: every rank must call it with the same arguments."""
         if self._symm_broken is not None or device.type != "cuda":
             return None
-        key = (Q, k, device.index)
+        key = (tag, tuple(shape), dtype, device.index)
         if key not in self._symm:
             buf, err = None, None
             try:
                 import torch.distributed._symmetric_memory as symm_mem
 
-                buf = symm_mem.empty((Q, k), dtype=torch.int64, device=device)
+                buf = symm_mem.empty(tuple(shape), dtype=dtype, device=device)
             except Exception as e:
                 err = "%s: %s" % (type(e).__name__, e)
             # the allocation is local, the rendezvous is collective: agree first so that no rank waits for one that gave up
@@ -686,12 +689,34 @@ class ShardedEvaluator:
                 if len(hdl.buffer_ptrs) != self.world:
                     raise RuntimeError("rendezvous returned %d buffers for %d ranks" % (len(hdl.buffer_ptrs), self.world))
                 if not (getattr(hdl, "has_multicast_support", False) and int(hdl.multicast_ptr)):
-                    raise RuntimeError("no NVSwitch multicast mapping for the key buffer (NVLS unavailable)")
+                    raise RuntimeError("no NVSwitch multicast mapping for the buffer (NVLS unavailable)")
                 self._symm[key] = (buf, hdl)
             except Exception as e:  # not supported here: remember why, use the NCCL exchange from now on
                 self._symm_broken = "%s: %s" % (type(e).__name__, e)
                 return None
         return self._symm[key]
+
+    def _symmetric_keys(self, Q: int, k: int, device):
+        return self._symmetric("keys", (Q, k), torch.int64, device)
+
+    def _gather_small(self, tag: str, t: torch.Tensor, nvls: bool) -> torch.Tensor:
+        """All-gather of a small per-rank block ([rows, Qpad] int32, ~1.3 MB) -> [world, rows, Qpad].  With NVSwitch multicast every
+        rank broadcasts its block into slot ``rank`` of a symmetric buffer with one store kernel between two device-side barriers
+        (peers are done reading the previous contents / all blocks have landed); the result aliases that buffer and stays valid
+        until the next gather with the same tag.  Otherwise (gloo, no multicast): NCCL / gloo all-gather."""
+        symm = None
+        if nvls and t.is_cuda and (t.numel() * t.element_size()) % 16 == 0:
+            symm = self._symmetric(tag, (self.world,) + tuple(t.shape), t.dtype, t.device)
+        if symm is None:
+            return self._gather(t)
+        buf, hdl = symm
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        hdl.barrier(channel=0)
+        with torch.cuda.device(t.device):
+            check(_lib.lib().cmh_nvls_broadcast(t.data_ptr(), int(hdl.multicast_ptr) + self.rank * nbytes, nbytes, _stream()))
+        hdl.barrier(channel=1)
+        return buf
 
     def exchange_info(self) -> Dict[str, object]:
         """What the top-k exchange uses in this process group (for logs / bench.py)."""
@@ -761,18 +786,20 @@ class ShardedEvaluator:
                 and candidate_path_ok(st, plan, n_geom, k) and self.world + 2 <= plan.Qpad):
             # (decided on the common geometry: same path on every rank)
             # candidate path: local cutoffs guarantee >= min(k, n_local) LOCAL candidates, hence every item of the global top-k
+            fused = method in ("auto", "nvls", "nvls_reduce", "peer_stores")
+            small_nvls = fused and os.environ.get("CMH_SMALL_EXCHANGE", "nvls") != "nccl"
             cap, cand, cnt, tot, meta = collect_candidates(
                 st, plan, ops, qp, gp_local, k, stages, idx_offset=idx_offset, rank=self.rank, world=self.world,
-                allreduce_sum=lambda t: self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group))
-            tot_all = self._gather(tot)                            # [world, bins + 1, Qpad]: per-distance totals + overflow flag
+                gather=lambda t: self._gather_small("sample", t, small_nvls))
+            tot_all = self._gather_small("totals", tot, small_nvls)  # [world, bins + 1, Qpad]: per-distance totals + overflow flag
             # verified on every rank from the same gathered data: no list overflowed, and the candidates of ALL ranks together
             # (a prefix of the global order) number at least min(k, gallery size) for every query
-            need = torch.clamp(meta[plan.bins, 1], max=k)
+            need = torch.clamp(meta[:, plan.bins, 1].sum(), max=k)
             short = (tot_all[:, : plan.bins, :Q].sum(dim=(0, 1)) < need).any()
             bad = short | (tot_all[:, plan.bins, 0].max() != 0)
             _mark(stages)
-            symm = self._symmetric_keys(Q, k, qp.device) if method in ("auto", "nvls", "peer_stores") else None
-            if method in ("nvls", "peer_stores") and symm is None:
+            symm = self._symmetric_keys(Q, k, qp.device) if fused else None
+            if method in ("nvls", "nvls_reduce", "peer_stores") and symm is None:
                 raise CmhError("%s exchange is not available: %s" % (method, self._symm_broken))
             if symm is not None and method == "peer_stores":
                 # fused place + exchange: a key's global slot is known, so the place kernel stores it straight into that slot of
@@ -787,7 +814,7 @@ class ShardedEvaluator:
                 hdl.barrier(channel=1)
                 keys = buf.clone() if copy else buf
                 _mark(stages)
-            elif symm is not None:
+            elif symm is not None and method == "nvls_reduce":
                 # The keys are placed into this rank's symmetric buffer (slots owned by other ranks stay EMPTY); then ONE kernel per
                 # rank reduces 1/world of the buffer in the switch (multimem.ld_reduce max) and broadcasts it (multimem.st).
                 # Barriers: peers must be done with the previous result before it is overwritten; all fills + placements must be
@@ -802,6 +829,21 @@ class ShardedEvaluator:
                 hdl.barrier(channel=2)
                 keys = buf.clone() if copy else buf
                 _mark(stages)
+            elif symm is not None:
+                # Default.  Every slot has exactly one owner: the keys are placed into this rank's symmetric buffer (other slots
+                # EMPTY), then each rank PUSHES the slots it owns to all ranks with coalesced multicast stores — no reduction, no
+                # round trip through the switch.  Only this rank reads its buffer, so no barrier is needed before the fill; a slot
+                # a peer's push already overwrote holds the final key and is pushed again unchanged.  Barriers: every rank has
+                # filled + placed before any push lands; all pushes have landed before anyone reads.
+                buf, hdl = symm
+                buf.fill_(EMPTY_KEY)
+                st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf)
+                hdl.barrier(channel=0)
+                with torch.cuda.device(qp.device):
+                    check(_lib.lib().cmh_nvls_push_owned_s64(buf.data_ptr(), int(hdl.multicast_ptr), buf.numel(), _stream()))
+                hdl.barrier(channel=1)
+                keys = buf.clone() if copy else buf
+                _mark(stages)
             else:
                 keys = torch.full((Q, k), EMPTY_KEY, dtype=torch.int64, device=qp.device)
                 st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys)
@@ -809,7 +851,7 @@ class ShardedEvaluator:
             if not bool(bad.item()):   # same answer on every rank
                 return keys
         hist = st.hist(plan, qp, None, gp_local, None, **kw)
-        if method in ("auto", "nvls", "peer_stores"):
+        if method in ("auto", "nvls", "nvls_reduce", "peer_stores"):
             method = "rank_scatter"                                 # the exact two-pass path exchanges through NCCL
         if method == "allgather_merge":
             sc = st.scan(plan, hist, 1, 0, k, with_rel=False)      # local ranking of this shard

@@ -215,10 +215,10 @@ int cmh_tc_rank_map(const cmh_plan* plan, const cmh_tc_operands* ops, const uint
  *                        The caller owns the synchronisation (a barrier over the ranks before and after). */
 int cmh_tc_topk_cutoff(const cmh_plan* sample_plan, const uint32_t* hist_sample, int64_t n_local, int64_t k, int32_t* cutoff,
                        int32_t* ibound, void* stream);
-/* Sharded form of the cutoff: sample_sum = SUM over the ranks of (this rank's sample histogram totals [bins][Qpad] | row `bins`:
- * [0] = its sample size, [1] = its shard size, [2 + r] = gallery index of its first item, written by rank r only), plain uint32
- * [bins + 1][Qpad].  One GLOBAL cutoff and index bound per query, the bound translated into this rank's shard: every rank keeps
- * ~k/world candidates and their union is a prefix of the global (distance, index) order. */
+/* Sharded form of the cutoff: sample_sum = the all-gathered blocks of all ranks, uint32 [world][bins + 1][Qpad]; rank r's block =
+ * its sample histogram totals [bins][Qpad] | row `bins`: [0] = its sample size, [1] = its shard size, [2 + r] = gallery index of its
+ * first item (cmh_tc_topk_sample_block).  One GLOBAL cutoff and index bound per query, the bound translated into this rank's
+ * shard: every rank keeps ~k/world candidates and their union is a prefix of the global (distance, index) order. */
 /* This rank's contribution to that sum, built by ONE kernel from its sample histogram (hist_sample may be NULL for an empty
  * shard): out[d][q] = sum over the sample chunks, out[bins][0..] = the header described above, everything else 0. */
 int cmh_tc_topk_sample_block(const cmh_plan* sample_plan, const uint32_t* hist_sample, int64_t Qpad, int bins, int64_t n_local,
@@ -242,6 +242,13 @@ int cmh_tc_topk_place(const cmh_plan* plan, int cand_cap, const uint32_t* cand, 
  * a barrier every rank's buffer holds the element-wise maximum.  Replaces the NCCL all-reduce(MAX) of the [Q][k] key buffer
  * (unowned slots are -1).  The caller brackets the call with barriers over the ranks. */
 int cmh_nvls_allreduce_max_s64(void* multicast_ptr, int64_t count, int rank, int world, void* stream);
+/* The same exchange without a reduction: every slot has one owner, so a rank pushes the slots it owns (everything that is not -1 in
+ * `local_keys`, its private placement buffer) into every rank's symmetric buffer with multicast stores.  The symmetric buffers
+ * must hold -1 (EMPTY) or stale data that will be overwritten: every one of the `count` slots is written by its owner. */
+int cmh_nvls_push_owned_s64(const void* local_keys, void* multicast_keys, int64_t count, void* stream);
+/* Broadcast `bytes` (multiple of 16) from local `src` to the same offset of every rank's symmetric buffer (multicast_dst already
+ * points at that offset): the all-gather of the small per-rank blocks (sample histograms, per-distance totals). */
+int cmh_nvls_broadcast(const void* src, void* multicast_dst, int64_t bytes, void* stream);
 
 /* ---- R5: merge of per-shard partial top-k after ONE all-gather -----------------------------------------
  * parts = [world][Q][k] sorted keys (0xFFFF...F = empty slot); out[q] = the k smallest keys. */

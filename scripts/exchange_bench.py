@@ -59,10 +59,24 @@ def nvls():
     hdl.barrier(channel=2)
 
 
+def push():
+    hdl.barrier(channel=0)
+    _lib.check(_lib.lib().cmh_nvls_push_owned_s64(buf.data_ptr(), int(hdl.multicast_ptr), buf.numel(), torch.cuda.current_stream().cuda_stream))
+    hdl.barrier(channel=1)
+
+
 if getattr(hdl, "has_multicast_support", False):
     timed("barrier + NVLS all-reduce(max) kernel + barrier", nvls)
+    timed("barrier + NVLS push-owned kernel + barrier", push)
+    timed("NVLS gather of the totals (2 barriers + bcast)", lambda: ev._gather_small("totals", tot, True))
     timed("fill(-1) of the [Q, k] buffer", lambda: buf.fill_(-1))
 timed("NCCL all-reduce(MAX) of the [Q, k] keys", lambda: dist.all_reduce(keys, op=dist.ReduceOp.MAX))
 timed("NCCL all-gather of the totals", lambda: ev._gather(tot))
 timed("clone of the [Q, k] buffer", lambda: buf.clone())
+for m in ("nvls", "nvls_reduce", "rank_scatter"):
+    for small in ("nvls", "nccl"):
+        os.environ["CMH_SMALL_EXCHANGE"] = small
+        timed("whole sharded top-k: keys %s, small exchanges %s" % (m, small),
+              lambda: ev.topk(qp, gp, K, k, lo, n_geom, method=m, copy=False), n=10)
+os.environ.pop("CMH_SMALL_EXCHANGE", None)
 dist.destroy_process_group()

@@ -174,6 +174,52 @@ def test_candidate_stages_sharded_equal_single(world):
     assert torch.equal(keys, want)
 
 
+@pytest.mark.parametrize("world,k", [(2, 1000), (4, 257), (3, 64)])
+def test_candidate_stages_global_cutoff_equal_single(world, k):
+    """the multi-GPU form with ONE global cutoff per query, simulated on one GPU: sample blocks of all shards gathered (stacked),
+    every shard derives the same cutoff and keeps ~k/world candidates, totals stacked like the all-gather, per-shard place into one
+    key buffer == single-GPU keys; the union of the candidates is enough for every query."""
+    Q, N, K = 300, 400_000, 64
+    qp = R.pack_codes(synth.random_codes(Q, K, 11).to(DEV))
+    gp = R.pack_codes(synth.random_codes(N, K, 12).to(DEV))
+    want = R.topk(qp, gp, K, k, exact=True)
+    st = R.CudaStages(True)
+    bounds = R.shard_bounds(N, world)
+    n_geom = max(hi - lo for lo, hi in bounds)
+    shards = []
+    for lo, hi in bounds:
+        plan = st.make_plan(Q, hi - lo, K, 0, n_geom)
+        shards.append((plan, lo, hi, st.operands(plan, qp, None, gp[lo:hi], None)))
+    blocks = []                                           # pass 1: every shard's own sample block (what it would send)
+    for r, (plan, lo, hi, ops) in enumerate(shards):
+        def capture(t):
+            blocks.append(t.clone())
+            return torch.stack([t] * world).contiguous()
+        R.collect_candidates(st, plan, ops, qp, gp[lo:hi], k, gather=capture, idx_offset=lo, rank=r, world=world)
+    gathered = torch.stack(blocks).contiguous()
+    bins = shards[0][0].bins
+    assert int(gathered[:, bins, 1].sum()) == N
+    parts = []
+    for r, (plan, lo, hi, ops) in enumerate(shards):       # pass 2: the real thing on the gathered blocks
+        cap, cand, cnt, tot, meta = R.collect_candidates(st, plan, ops, qp, gp[lo:hi], k, gather=lambda t: gathered,
+                                                         idx_offset=lo, rank=r, world=world)
+        parts.append((plan, lo, cap, cand, cnt, tot))
+    tot_all = torch.stack([p[5] for p in parts]).contiguous()
+    assert int(tot_all[:, bins, 0].max()) == 0                                  # no list overflowed
+    per_query = tot_all[:, :bins, :Q].sum(dim=(0, 1))
+    assert int(per_query.min()) >= k                                            # together: enough for every query
+    assert float(per_query.float().mean()) < 2.5 * k + 200                      # ... and about k of them, not world x k
+    keys = torch.full((Q, k), R.EMPTY_KEY, dtype=torch.int64, device=DEV)
+    for r, (plan, lo, cap, cand, cnt, tot) in enumerate(parts):
+        mine = torch.full((Q, k), R.EMPTY_KEY, dtype=torch.int64, device=DEV)
+        st.topk_place(plan, cap, cand, cnt, tot_all, world, r, k, lo, mine)
+        assert int(((mine != R.EMPTY_KEY) & (keys != R.EMPTY_KEY)).sum()) == 0
+        keys = torch.maximum(keys, mine)
+    assert torch.equal(keys, want)
+    with pytest.raises(R.CmhError):                                             # one block instead of the gathered blocks
+        st.topk_cutoff_sharded(shards[0][0], gathered[0], k, 0, world)
+
+
 def test_topk_from_host_slab_pipeline_equals_resident_path():
     """host +-1 fp32 codes streamed in slabs (H2D overlapped with pack / expand / collect) == codes resident on the GPU."""
     from clip_based_cross_modal_hash_b200 import calc_utils as cu
