@@ -232,10 +232,13 @@ class Dist:
             self.dist.destroy_process_group()
 
 
+GRAPH_LAUNCHES = [0]   # kernels of libcmh.so launched through CUDA-graph replays (the library's counter only sees stream launches)
+
+
 def launches():
     from clip_based_cross_modal_hash_b200 import _lib
 
-    return int(_lib.lib().cmh_launch_count())
+    return int(_lib.lib().cmh_launch_count()) + GRAPH_LAUNCHES[0]
 
 
 def survey_roofline(Q, N_local, K, k, t_ms, peaks, sm_mhz, op="topk", C=0):
@@ -305,30 +308,65 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
         mark()
         return keys
 
-    for _ in range(max(warmup, 3)):
-        step()
-        flush.zero_()
-    D.barrier()
-    l0 = launches()
-    per_step, stage_ms, host_ms = [], None, 0.0
-    with ClockSampler(D.local_rank) as clocks:
-        D.barrier()
-        for _ in range(steps):
+    # The timed step is ONE CUDA-graph replay of pack -> ... -> place (retrieval.TopkGraph) + its status read-back; the same step
+    # queued eagerly, launch by launch, is timed afterwards for the per-stage breakdown and the host cost it carries.
+    graph = None
+    if not args.no_graph:
+        try:
+            graph = R.TopkGraph(d_qB, d_rB, k, evaluator=ev, idx_offset=lo if world > 1 else 0,
+                                n_geom=n_geom if world > 1 else None, method=args.topk_exchange)
+        except R.CmhError:
+            graph = None           # shape outside the candidate path (decided on the common geometry: same on every rank)
+
+    def timed(fn, with_stages):
+        for _ in range(max(warmup, 3)):
+            fn(None)
             flush.zero_()
-            evs = []
-            h0 = time.perf_counter()
-            keys = step(evs)
-            host_ms += (time.perf_counter() - h0) * 1e3     # host time to queue one step (launch-bound if close to ms_per_step)
-            torch.cuda.synchronize()
-            per_step.append(evs[0].elapsed_time(evs[-1]))
-            if want_stage:
-                d = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]
-                stage_ms = d if (stage_ms is None or len(stage_ms) != len(d)) else [a + b for a, b in zip(stage_ms, d)]
         D.barrier()
+        per_step, stage_ms, host_ms = [], None, 0.0
+        with ClockSampler(D.local_rank) as clocks:
+            D.barrier()
+            for _ in range(steps):
+                flush.zero_()
+                evs = []
+                h0 = time.perf_counter()
+                keys = fn(evs)
+                host_ms += (time.perf_counter() - h0) * 1e3     # host time to queue one step (launch-bound if close to ms_per_step)
+                torch.cuda.synchronize()
+                per_step.append(evs[0].elapsed_time(evs[-1]))
+                if with_stages:
+                    d = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]
+                    stage_ms = d if (stage_ms is None or len(stage_ms) != len(d)) else [a + b for a, b in zip(stage_ms, d)]
+            D.barrier()
+        return keys, D.all_max(sum(per_step)), stage_ms, host_ms, clocks
+
+    def graph_step(events):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        keys = graph.run()
+        e1.record()
+        GRAPH_LAUNCHES[0] += graph.kernels
+        if events is not None:
+            events += [e0, e1]
+        return keys
+
+    l0 = launches()
+    eager_keys, eager_ms, stage_ms, host_ms, clocks = timed(step, want_stage) if (graph is None or want_stage) else (None, None, None, 0.0, None)
     n_launch = launches() - l0
-    total_ms = D.all_max(sum(per_step))
+    if graph is not None:
+        keys, total_ms, _, graph_host_ms, clocks = timed(graph_step, False)
+        n_launch = graph.kernels * steps                     # kernels of this library inside the timed replays
+        if eager_keys is not None and not torch.equal(eager_keys, keys):
+            raise SystemExit("graph replay and eager step disagree")
+    else:
+        keys, total_ms = eager_keys, eager_ms
     out = {"bits": K, "ms_per_step": total_ms / steps, "value": Q * n_total * steps / (total_ms * 1e-3), "steps": steps,
-           "clocks": clocks.summary(), "gpu_launches": n_launch}
+           "clocks": clocks.summary(), "gpu_launches": n_launch,
+           "step": "one CUDA-graph replay + status read-back" if graph is not None else "eager launches"}
+    if graph is not None:
+        out["graph"] = {"kernels_per_replay": graph.kernels, "host_ms_per_step_incl_status_wait": graph_host_ms / steps}
+        if eager_ms is not None:
+            out["eager_ms_per_step"] = eager_ms / steps
 
     # untimed parity check of the last step's result (rank 0 holds the full gallery in strong mode)
     if scaling == "strong" or world == 1:
@@ -344,6 +382,7 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
         else:
             names = R.TOPK_FAST_STAGE_NAMES if len(stage_ms) == 7 else R.TOPK_STAGE_NAMES
         out["stage_ms"] = {"pack": stage_ms[0] / steps, **{n: v / steps for n, v in zip(names, stage_ms[1:])}}
+        out["stage_ms_note"] = "measured on the eager step (events cannot be timed inside a graph replay)"
         out["host_ms_per_step"] = host_ms / steps
     if ev is not None:
         out["exchange_info"] = ev.exchange_info()
@@ -711,6 +750,9 @@ def run_ours(args, cfg, name):
     if args.op == "topk":
         line["exchange"] = {"method": args.topk_exchange, **head.get("exchange_info", {})} if world > 1 else None
         line["parity_check"] = head.get("parity_check")
+        for key in ("step", "graph", "eager_ms_per_step", "stage_ms_note"):
+            if key in head:
+                line[key] = head[key]
         dom, dom_ms = None, None
         if "stage_ms" in head:
             line["stage_ms"] = head["stage_ms"]
@@ -781,6 +823,7 @@ def main():
     ap.add_argument("--workload", default="C4-64", choices=sorted(synth.CONFIGS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="top-k only: strong = the workload's gallery split over the GPUs (default), weak = one full gallery per GPU")
+    ap.add_argument("--no-graph", action="store_true", help="time the eagerly launched step instead of the CUDA-graph replay")
     ap.add_argument("--topk-exchange", default="auto", choices=["auto", "nvls", "nvls_reduce", "peer_stores", "rank_scatter", "allgather_merge"])
     ap.add_argument("--no-encode", action="store_true", help="skip the CLIP encode section of the line")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 16/32/128-bit sweep")

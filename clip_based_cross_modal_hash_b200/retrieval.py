@@ -641,6 +641,9 @@ def shard_bounds(n: int, world: int, align: int = 4) -> List[Tuple[int, int]]:
     return [(min(r * per, n), min((r + 1) * per, n)) for r in range(world)]
 
 
+TOPK_EXCHANGES = ("auto", "nvls", "nvls_reduce", "peer_stores", "rank_scatter", "allgather_merge")
+
+
 class ShardedEvaluator:
     """mAP / top-k with the gallery sharded over ``group``; queries (and their labels) are replicated.
 
@@ -763,6 +766,84 @@ class ShardedEvaluator:
             self.dist.all_reduce(tindex, op=self.dist.ReduceOp.SUM, group=self.group)
         return MapResult(m, ap, sc["tsum"][:Q], sc["total"][:Q], tindex)
 
+    def candidate_path(self, plan: Plan, ops, n_geom: int, k: int, method: str = "auto") -> bool:
+        """Whether the single-pass candidate path applies (decided on the common geometry: same answer on every rank)."""
+        st = self.stages
+        return (method != "allgather_merge" and ops is not None and candidate_path_ok(st, plan, n_geom, k)
+                and self.world + 2 <= plan.Qpad)
+
+    def _topk_candidates(self, plan: Plan, ops, qp, gp_local, k: int, idx_offset: int, n_geom: int, method: str, copy: bool,
+                         stages: Optional[list]):
+        """The candidate path of ``topk`` without any host synchronisation (it is also what ``TopkGraph`` captures): returns
+        ``(keys, bad)``; ``bad`` is a device bool — a candidate list overflowed or the candidates of all ranks together were too few
+        for some query — and the caller must then take the exact path.  Local cutoffs come from ONE global sample, so the
+        candidates of all ranks are a prefix of the global (distance, index) order."""
+        st = self.stages
+        Q = plan.Q
+        fused = method in ("auto", "nvls", "nvls_reduce", "peer_stores")
+        small_nvls = fused and os.environ.get("CMH_SMALL_EXCHANGE", "nvls") != "nccl"
+        cap, cand, cnt, tot, meta = collect_candidates(
+            st, plan, ops, qp, gp_local, k, stages, idx_offset=idx_offset, rank=self.rank, world=self.world,
+            gather=lambda t: self._gather_small("sample", t, small_nvls))
+        tot_all = self._gather_small("totals", tot, small_nvls)  # [world, bins + 1, Qpad]: per-distance totals + overflow flag
+        # verified on every rank from the same gathered data: no list overflowed, and the candidates of ALL ranks together
+        # (a prefix of the global order) number at least min(k, gallery size) for every query
+        need = torch.clamp(meta[:, plan.bins, 1].sum(), max=k)
+        short = (tot_all[:, : plan.bins, :Q].sum(dim=(0, 1)) < need).any()
+        bad = short | (tot_all[:, plan.bins, 0].max() != 0)
+        _mark(stages)
+        symm = self._symmetric_keys(Q, k, qp.device) if fused else None
+        if method in ("nvls", "nvls_reduce", "peer_stores") and symm is None:
+            raise CmhError("%s exchange is not available: %s" % (method, self._symm_broken))
+        if symm is not None and method == "peer_stores":
+            # fused place + exchange: a key's global slot is known, so the place kernel stores it straight into that slot of
+            # every rank's buffer over NVLink.  Correct, but scattered 8-byte remote stores run at a fraction of the link rate
+            # (2 GPUs: 0.69 ms against 0.16 ms local placement + 0.1 ms NVLS reduction, profiles/README.md): not the default.
+            buf, hdl = symm
+            if k > n_geom * self.world:
+                buf.fill_(EMPTY_KEY)
+            hdl.barrier(channel=0)
+            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, None,
+                          peers_dev=int(hdl.buffer_ptrs_dev), npeers=self.world)
+            hdl.barrier(channel=1)
+            keys = buf.clone() if copy else buf
+            _mark(stages)
+        elif symm is not None and method == "nvls_reduce":
+            # The keys are placed into this rank's symmetric buffer (slots owned by other ranks stay EMPTY); then ONE kernel per
+            # rank reduces 1/world of the buffer in the switch (multimem.ld_reduce max) and broadcasts it (multimem.st).
+            # Barriers: peers must be done with the previous result before it is overwritten; all fills + placements must be
+            # visible before the reduction; all broadcasts must have landed before anyone reads.
+            buf, hdl = symm
+            hdl.barrier(channel=0)
+            buf.fill_(EMPTY_KEY)
+            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf)
+            hdl.barrier(channel=1)
+            with torch.cuda.device(qp.device):
+                check(_lib.lib().cmh_nvls_allreduce_max_s64(int(hdl.multicast_ptr), buf.numel(), self.rank, self.world, _stream()))
+            hdl.barrier(channel=2)
+            keys = buf.clone() if copy else buf
+            _mark(stages)
+        elif symm is not None:
+            # Default.  Every slot has exactly one owner: the keys are placed into this rank's symmetric buffer (other slots
+            # EMPTY), then each rank PUSHES the slots it owns to all ranks with coalesced multicast stores — no reduction, no
+            # round trip through the switch.  Only this rank reads its buffer, so no barrier is needed before the fill; a slot
+            # a peer's push already overwrote holds the final key and is pushed again unchanged.  Barriers: every rank has
+            # filled + placed before any push lands; all pushes have landed before anyone reads.
+            buf, hdl = symm
+            buf.fill_(EMPTY_KEY)
+            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf)
+            hdl.barrier(channel=0)
+            with torch.cuda.device(qp.device):
+                check(_lib.lib().cmh_nvls_push_owned_s64(buf.data_ptr(), int(hdl.multicast_ptr), buf.numel(), _stream()))
+            hdl.barrier(channel=1)
+            keys = buf.clone() if copy else buf
+            _mark(stages)
+        else:
+            keys = torch.full((Q, k), EMPTY_KEY, dtype=torch.int64, device=qp.device)
+            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys)
+            self._exchange_keys(keys, method)
+        return keys, bad
+
     def topk(self, qp, gp_local, nbits: int, k: int, idx_offset: int, n_geom: Optional[int] = None,
              method: str = "auto", exact: Optional[bool] = None, copy: bool = True, stages: Optional[list] = None) -> torch.Tensor:
         """Global top-k keys [Q, k] (identical on every rank) of a gallery sharded by contiguous index range.
@@ -776,78 +857,16 @@ class ShardedEvaluator:
         """
         st = self.stages
         k = _check_k(k)
+        if method not in TOPK_EXCHANGES:
+            raise CmhError("unknown top-k exchange %r" % method)
         Q, n_local = qp.shape[0], gp_local.shape[0]
         n_geom = self._geometry(n_local, n_geom, qp.device)
         plan = st.make_plan(Q, n_local, nbits, 0, n_geom)
         ops = st.operands(plan, qp, None, gp_local, None) if hasattr(st, "operands") else None
         _mark(stages)
         kw = {"ops": ops} if ops is not None else {}
-        if (method != "allgather_merge" and exact is not True and ops is not None
-                and candidate_path_ok(st, plan, n_geom, k) and self.world + 2 <= plan.Qpad):
-            # (decided on the common geometry: same path on every rank)
-            # candidate path: local cutoffs guarantee >= min(k, n_local) LOCAL candidates, hence every item of the global top-k
-            fused = method in ("auto", "nvls", "nvls_reduce", "peer_stores")
-            small_nvls = fused and os.environ.get("CMH_SMALL_EXCHANGE", "nvls") != "nccl"
-            cap, cand, cnt, tot, meta = collect_candidates(
-                st, plan, ops, qp, gp_local, k, stages, idx_offset=idx_offset, rank=self.rank, world=self.world,
-                gather=lambda t: self._gather_small("sample", t, small_nvls))
-            tot_all = self._gather_small("totals", tot, small_nvls)  # [world, bins + 1, Qpad]: per-distance totals + overflow flag
-            # verified on every rank from the same gathered data: no list overflowed, and the candidates of ALL ranks together
-            # (a prefix of the global order) number at least min(k, gallery size) for every query
-            need = torch.clamp(meta[:, plan.bins, 1].sum(), max=k)
-            short = (tot_all[:, : plan.bins, :Q].sum(dim=(0, 1)) < need).any()
-            bad = short | (tot_all[:, plan.bins, 0].max() != 0)
-            _mark(stages)
-            symm = self._symmetric_keys(Q, k, qp.device) if fused else None
-            if method in ("nvls", "nvls_reduce", "peer_stores") and symm is None:
-                raise CmhError("%s exchange is not available: %s" % (method, self._symm_broken))
-            if symm is not None and method == "peer_stores":
-                # fused place + exchange: a key's global slot is known, so the place kernel stores it straight into that slot of
-                # every rank's buffer over NVLink.  Correct, but scattered 8-byte remote stores run at a fraction of the link rate
-                # (2 GPUs: 0.69 ms against 0.16 ms local placement + 0.1 ms NVLS reduction, profiles/README.md): not the default.
-                buf, hdl = symm
-                if k > n_geom * self.world:
-                    buf.fill_(EMPTY_KEY)
-                hdl.barrier(channel=0)
-                st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, None,
-                              peers_dev=int(hdl.buffer_ptrs_dev), npeers=self.world)
-                hdl.barrier(channel=1)
-                keys = buf.clone() if copy else buf
-                _mark(stages)
-            elif symm is not None and method == "nvls_reduce":
-                # The keys are placed into this rank's symmetric buffer (slots owned by other ranks stay EMPTY); then ONE kernel per
-                # rank reduces 1/world of the buffer in the switch (multimem.ld_reduce max) and broadcasts it (multimem.st).
-                # Barriers: peers must be done with the previous result before it is overwritten; all fills + placements must be
-                # visible before the reduction; all broadcasts must have landed before anyone reads.
-                buf, hdl = symm
-                hdl.barrier(channel=0)
-                buf.fill_(EMPTY_KEY)
-                st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf)
-                hdl.barrier(channel=1)
-                with torch.cuda.device(qp.device):
-                    check(_lib.lib().cmh_nvls_allreduce_max_s64(int(hdl.multicast_ptr), buf.numel(), self.rank, self.world, _stream()))
-                hdl.barrier(channel=2)
-                keys = buf.clone() if copy else buf
-                _mark(stages)
-            elif symm is not None:
-                # Default.  Every slot has exactly one owner: the keys are placed into this rank's symmetric buffer (other slots
-                # EMPTY), then each rank PUSHES the slots it owns to all ranks with coalesced multicast stores — no reduction, no
-                # round trip through the switch.  Only this rank reads its buffer, so no barrier is needed before the fill; a slot
-                # a peer's push already overwrote holds the final key and is pushed again unchanged.  Barriers: every rank has
-                # filled + placed before any push lands; all pushes have landed before anyone reads.
-                buf, hdl = symm
-                buf.fill_(EMPTY_KEY)
-                st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf)
-                hdl.barrier(channel=0)
-                with torch.cuda.device(qp.device):
-                    check(_lib.lib().cmh_nvls_push_owned_s64(buf.data_ptr(), int(hdl.multicast_ptr), buf.numel(), _stream()))
-                hdl.barrier(channel=1)
-                keys = buf.clone() if copy else buf
-                _mark(stages)
-            else:
-                keys = torch.full((Q, k), EMPTY_KEY, dtype=torch.int64, device=qp.device)
-                st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys)
-                self._exchange_keys(keys, method)
+        if exact is not True and self.candidate_path(plan, ops, n_geom, k, method):
+            keys, bad = self._topk_candidates(plan, ops, qp, gp_local, k, idx_offset, n_geom, method, copy, stages)
             if not bool(bad.item()):   # same answer on every rank
                 return keys
         hist = st.hist(plan, qp, None, gp_local, None, **kw)
@@ -858,8 +877,6 @@ class ShardedEvaluator:
             keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset, **kw)
             parts = self._gather(keys)                             # [world, Q, k]
             return st.topk_merge(parts)
-        if method != "rank_scatter":
-            raise CmhError("unknown top-k exchange %r" % method)
         totals_all = self._gather(st.hist_totals(plan, hist))      # [world, 2, bins, Qpad]
         sc = st.scan_sharded(plan, hist, totals_all, self.world, self.rank, k)
         keys = st.rank_topk(plan, qp, gp_local, sc, k, idx_offset, **kw)  # slots of global rank < k owned by this shard
@@ -869,3 +886,100 @@ class ShardedEvaluator:
     def _exchange_keys(self, keys: torch.Tensor, method: str) -> None:
         """Every slot of the [Q, k] key buffer is owned by exactly one rank (the others hold EMPTY = -1 < every real key)."""
         self.dist.all_reduce(keys, op=self.dist.ReduceOp.MAX, group=self.group)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the whole top-k step as ONE CUDA graph
+# ---------------------------------------------------------------------------------------------------------
+class TopkGraph:
+    """pack -> expand -> sample histogram -> cutoff -> collect -> count -> (exchanges) -> place, captured once as a CUDA graph over
+    static buffers and replayed per evaluation.
+
+    Why: the step is ~20 launches of 10-900 us.  Queued one by one through Python the host needs 1-2 ms per step — at 8 GPUs that
+    is longer than the GPU work (0.3 ms of collect per shard), every rank's launches trail its kernels, and each exchange turns
+    into a wait for the slowest HOST.  Replayed as a graph the step costs one launch; with the NVSwitch multicast exchanges
+    (`_gather_small`, push-owned keys) it contains no NCCL call at all, only kernels and device-side barriers.
+
+    ``q_codes`` [Q, K] / ``g_codes`` [N_local, K]: +-1 fp32 CUDA tensors that STAY the inputs of every replay — refresh them in
+    place (``copy_``) between runs.  ``evaluator``: a ShardedEvaluator when the gallery is sharded over a process group
+    (``idx_offset`` = global index of this shard's first item, ``n_geom`` = the largest shard); every rank must build and run the
+    graph together.  ``run()`` returns the int64 ``(dist << 32) | index`` keys [Q, k] — a static buffer, overwritten by the next
+    run; if the device-side verification fails (cutoff too tight for some query, a candidate list overflowed) it falls back to
+    the exact two-pass path, and it raises ValueError for codes that are not +-1, like ``calc_utils.hamming_topk``."""
+
+    def __init__(self, q_codes: torch.Tensor, g_codes: torch.Tensor, k: int, evaluator: Optional["ShardedEvaluator"] = None,
+                 idx_offset: int = 0, n_geom: Optional[int] = None, method: str = "auto"):
+        dev = _need_cuda(q_codes, g_codes)
+        if q_codes.dtype != torch.float32 or g_codes.dtype != torch.float32 or not (q_codes.is_contiguous() and g_codes.is_contiguous()):
+            raise CmhError("TopkGraph: static code buffers must be contiguous fp32")
+        self.q, self.g, self.k, self.ev = q_codes, g_codes, _check_k(k), evaluator
+        self.idx_offset, self.method = int(idx_offset), method
+        self.nbits = q_codes.shape[1]
+        self.st = evaluator.stages if evaluator is not None else CudaStages()
+        Q, n_local = q_codes.shape[0], g_codes.shape[0]
+        if evaluator is not None:
+            if method not in ("auto", "nvls", "nvls_reduce", "peer_stores", "rank_scatter"):
+                raise CmhError("TopkGraph: exchange %r has no single-pass form" % method)
+            self.n_geom = evaluator._geometry(n_local, n_geom, dev)
+        else:
+            self.n_geom = n_local
+        self.plan = self.st.make_plan(Q, n_local, self.nbits, 0, self.n_geom if evaluator is not None else None)
+        if not candidate_path_ok(self.st, self.plan, self.n_geom, self.k) or (evaluator is not None and evaluator.world + 2 > self.plan.Qpad):
+            raise CmhError("TopkGraph: the single-pass candidate path does not apply to this shape (use topk)")
+        self.status = torch.zeros(2, dtype=torch.int64, device=dev)     # [0] path failed, [1] elements that are not +-1
+        self._bad_codes = new_bad_counter(dev)
+        self.keys = None
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):   # eager warm-up on the capture stream: symmetric buffers, kernel attributes, allocator pool
+                    self._body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            l0 = int(_lib.lib().cmh_launch_count())
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self._body()
+            self.kernels = int(_lib.lib().cmh_launch_count()) - l0       # launches of this library inside one replay
+        self._pin = torch.empty(2, dtype=torch.int64).pin_memory()
+
+    def _body(self) -> None:
+        st, plan, k = self.st, self.plan, self.k
+        self._bad_codes.zero_()
+        qp = pack_codes(self.q, self._bad_codes)
+        gp = pack_codes(self.g, self._bad_codes)
+        ops = st.operands(plan, qp, None, gp, None)
+        if self.ev is None:
+            cap, cand, cnt, tot, _ = collect_candidates(st, plan, ops, qp, gp, k)
+            if self.keys is None:
+                self.keys = torch.empty((plan.Q, k), dtype=torch.int64, device=qp.device)
+            st.topk_place(plan, cap, cand, cnt, tot, 1, 0, k, self.idx_offset, self.keys)
+            failed = tot[plan.bins, 0] != 0
+        else:
+            self.keys, failed = self.ev._topk_candidates(plan, ops, qp, gp, k, self.idx_offset, self.n_geom, self.method, False, None)
+        self.status[0] = failed
+        self.status[1] = self._bad_codes[0]
+
+    def replay(self) -> torch.Tensor:
+        """Queue one step on the current stream; no host synchronisation, no verification (``run`` does both)."""
+        self.graph.replay()
+        return self.keys
+
+    def run(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.finish()
+
+    def finish(self) -> torch.Tensor:
+        """Verification of the last replay: reads the two status words (the one host synchronisation of a step)."""
+        self._pin.copy_(self.status, non_blocking=True)
+        torch.cuda.current_stream(self.q.device).synchronize()
+        failed, bad = int(self._pin[0]), int(self._pin[1])
+        if bad:
+            raise ValueError("TopkGraph: codes must be +-1")
+        if not failed:
+            return self.keys
+        qp, gp = pack_codes(self.q), pack_codes(self.g)               # same decision on every rank (gathered totals)
+        if self.ev is None:
+            return topk(qp, gp, self.nbits, self.k, self.idx_offset, exact=True)
+        return self.ev.topk(qp, gp, self.nbits, self.k, self.idx_offset, self.n_geom, method=self.method, exact=True)

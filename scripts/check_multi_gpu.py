@@ -64,6 +64,19 @@ def main():
     outs["auto, zero-copy result"] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo, copy=False), want))
     if ev.exchange_info().get("peer_memory"):
         outs["peer_stores"] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo, method="peer_stores"), want))
+        outs["nvls_reduce"] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo, method="nvls_reduce"), want))
+    outs["rank_scatter"] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo, method="rank_scatter"), want))
+    # the whole sharded step as one CUDA graph per rank, replayed on refreshed static inputs
+    n_geom = max(b - a for a, b in R.shard_bounds(N, world))
+    q_codes = synth.random_codes(Q, K, 5).to(dev)
+    g_codes = synth.random_codes(N, K, 6)[lo:hi].contiguous().to(dev)
+    graph = R.TopkGraph(q_codes, g_codes, kk, evaluator=ev, idx_offset=lo, n_geom=n_geom)
+    outs["graph"] = bool(torch.equal(graph.run(), want))
+    g2 = synth.random_codes(N, K, 66)
+    g_codes.copy_(g2[lo:hi].to(dev))
+    want2 = R.topk(qp, R.pack_codes(g2.to(dev)), K, kk, exact=True)
+    outs["graph, replay on a new gallery"] = bool(torch.equal(graph.run(), want2))
+    outs["eager after graph"] = bool(torch.equal(ev.topk(qp, gp[lo:hi], K, kk, lo), want))
     if rank == 0:
         print("fused exchange world=%d: %s  %s" % (world, outs, ev.exchange_info()), flush=True)
     ok = ok and all(outs.values())

@@ -238,3 +238,28 @@ def test_topk_from_host_slab_pipeline_equals_resident_path():
     bad[N - 5, 3] = 0.0                                        # a non +-1 element in the LAST slab is still reported
     with pytest.raises(ValueError):
         cu.hamming_topk(qB, bad, k)
+
+
+def test_topk_graph_replays_equal_exact_path():
+    """the whole step captured as one CUDA graph: replays on refreshed static inputs == the exact two-pass path; the device-side
+    verification still routes a failed candidate pass to the exact path; codes that are not +-1 are reported."""
+    Q, N, K, k = 400, 300_000, 64, 500
+    q = synth.random_codes(Q, K, 81).to(DEV)
+    g = synth.random_codes(N, K, 82).to(DEV)
+    graph = R.TopkGraph(q, g, k)
+    assert graph.kernels >= 8
+    for seed in (82, 83, 84):
+        g.copy_(synth.random_codes(N, K, seed).to(DEV))          # refreshed in place: same buffers, new gallery
+        want = R.topk(R.pack_codes(q), R.pack_codes(g), K, k, exact=True)
+        assert torch.equal(graph.run(), want)
+    # a gallery whose sample prefix looks nothing like the rest: cutoffs too tight -> flagged on the device -> exact path
+    near = synth.random_codes(1, K, 8).to(DEV)
+    g[N - 40_000:] = near
+    q[:100] = near
+    want = R.topk(R.pack_codes(q), R.pack_codes(g), K, k, exact=True)
+    assert torch.equal(graph.run(), want)
+    g[17, 5] = 0.5
+    with pytest.raises(ValueError):
+        graph.run()
+    with pytest.raises(R.CmhError):                                # too small for the candidate path
+        R.TopkGraph(q[:10], g[:1000].contiguous(), 100)
