@@ -119,7 +119,7 @@ PROTOTYPES = {
     "cmh_tc_topk_cutoff_sharded": [_PP, _vp, _i64, _i32, _i32, _vp, _vp, _vp],
     "cmh_tc_topk_collect": [_PP, _OP, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp],
     "cmh_tc_topk_count": [_PP, _i32, _vp, _vp, _i64, _vp, _vp, _vp],
-    "cmh_tc_topk_place": [_PP, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _vp],
+    "cmh_tc_topk_place": [_PP, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
     "cmh_nvls_allreduce_max_s64": [_vp, _i64, _i32, _i32, _vp],
     "cmh_nvls_push_owned_s64": [_vp, _vp, _i64, _vp],
     "cmh_nvls_broadcast": [_vp, _vp, _i64, _vp],

@@ -377,13 +377,17 @@ class CudaStages:
 
     def topk_place(self, plan: Plan, cap: int, cand: torch.Tensor, cnt: torch.Tensor, totals_all: torch.Tensor, world: int,
                    rank: int, k: int, idx_offset: int, keys: Optional[torch.Tensor], peers_dev: Optional[int] = None, npeers: int = 0,
-                   multicast: Optional[int] = None) -> Optional[torch.Tensor]:
+                   multicast: Optional[int] = None, verify: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                   ) -> Optional[torch.Tensor]:
         """``peers_dev``: device address of a table of ``npeers`` peer-mapped [Q, k] key buffers (one per rank); ``multicast``: the
-        NVSwitch multicast address of those buffers.  With either, the keys go straight into every rank's buffer."""
+        NVSwitch multicast address of those buffers.  With either, the keys go straight into every rank's buffer.
+        ``verify=(sample_all, status)``: sharded verification inside the same kernel — ``status`` (int32[1]) gets bit 0 set when a
+        rank overflowed a list or the candidates of all ranks are too few (``sample_all`` = the gathered sample blocks)."""
+        sample_all, status = verify if verify is not None else (None, None)
         with torch.cuda.device(cand.device):
             check(_lib.lib().cmh_tc_topk_place(ctypes.byref(plan), cap, cand.data_ptr(), cnt.data_ptr(), totals_all.data_ptr(),
                                                (plan.bins + 1) * plan.Qpad, world, rank, k, idx_offset, _ptr(keys), peers_dev, npeers,
-                                               multicast, _stream()))
+                                               multicast, _ptr(sample_all), _ptr(status), _stream()))
         return keys
 
     def topk_merge(self, parts: torch.Tensor) -> torch.Tensor:
@@ -702,11 +706,13 @@ class ShardedEvaluator:
     def _symmetric_keys(self, Q: int, k: int, device):
         return self._symmetric("keys", (Q, k), torch.int64, device)
 
-    def _gather_small(self, tag: str, t: torch.Tensor, nvls: bool) -> torch.Tensor:
-        """All-gather of a small per-rank block ([rows, Qpad] int32, ~1.3 MB) -> [world, rows, Qpad].  With NVSwitch multicast every
+    def _gather_small(self, tag: str, t: torch.Tensor, nvls: bool, pre_barrier: bool = True) -> torch.Tensor:
+        """All-gather of a small per-rank block ([rows, Qpad] int32, ~2.7 MB) -> [world, rows, Qpad].  With NVSwitch multicast every
         rank broadcasts its block into slot ``rank`` of a symmetric buffer with one store kernel between two device-side barriers
         (peers are done reading the previous contents / all blocks have landed); the result aliases that buffer and stays valid
-        until the next gather with the same tag.  Otherwise (gloo, no multicast): NCCL / gloo all-gather."""
+        until the next gather with the same tag.  ``pre_barrier=False``: the caller guarantees that every rank passes another
+        barrier of the group between its last read of this buffer and the next gather (the sharded top-k does: the barriers of
+        the key exchange follow the kernels that read the gathered blocks).  Otherwise (gloo, no multicast): NCCL / gloo all-gather."""
         symm = None
         if nvls and t.is_cuda and (t.numel() * t.element_size()) % 16 == 0:
             symm = self._symmetric(tag, (self.world,) + tuple(t.shape), t.dtype, t.device)
@@ -715,7 +721,8 @@ class ShardedEvaluator:
         buf, hdl = symm
         t = t.contiguous()
         nbytes = t.numel() * t.element_size()
-        hdl.barrier(channel=0)
+        if pre_barrier:
+            hdl.barrier(channel=0)
         with torch.cuda.device(t.device):
             check(_lib.lib().cmh_nvls_broadcast(t.data_ptr(), int(hdl.multicast_ptr) + self.rank * nbytes, nbytes, _stream()))
         hdl.barrier(channel=1)
@@ -775,26 +782,28 @@ class ShardedEvaluator:
     def _topk_candidates(self, plan: Plan, ops, qp, gp_local, k: int, idx_offset: int, n_geom: int, method: str, copy: bool,
                          stages: Optional[list]):
         """The candidate path of ``topk`` without any host synchronisation (it is also what ``TopkGraph`` captures): returns
-        ``(keys, bad)``; ``bad`` is a device bool — a candidate list overflowed or the candidates of all ranks together were too few
-        for some query — and the caller must then take the exact path.  Local cutoffs come from ONE global sample, so the
-        candidates of all ranks are a prefix of the global (distance, index) order."""
+        ``(keys, bad)``; ``bad`` is a device int32[1], non-zero when a candidate list overflowed or the candidates of all ranks
+        together were too few for some query — and the caller must then take the exact path.  Local cutoffs come from ONE global
+        sample, so the candidates of all ranks are a prefix of the global (distance, index) order."""
         st = self.stages
         Q = plan.Q
         fused = method in ("auto", "nvls", "nvls_reduce", "peer_stores")
         small_nvls = fused and os.environ.get("CMH_SMALL_EXCHANGE", "nvls") != "nccl"
-        cap, cand, cnt, tot, meta = collect_candidates(
-            st, plan, ops, qp, gp_local, k, stages, idx_offset=idx_offset, rank=self.rank, world=self.world,
-            gather=lambda t: self._gather_small("sample", t, small_nvls))
-        tot_all = self._gather_small("totals", tot, small_nvls)  # [world, bins + 1, Qpad]: per-distance totals + overflow flag
-        # verified on every rank from the same gathered data: no list overflowed, and the candidates of ALL ranks together
-        # (a prefix of the global order) number at least min(k, gallery size) for every query
-        need = torch.clamp(meta[:, plan.bins, 1].sum(), max=k)
-        short = (tot_all[:, : plan.bins, :Q].sum(dim=(0, 1)) < need).any()
-        bad = short | (tot_all[:, plan.bins, 0].max() != 0)
-        _mark(stages)
         symm = self._symmetric_keys(Q, k, qp.device) if fused else None
         if method in ("nvls", "nvls_reduce", "peer_stores") and symm is None:
             raise CmhError("%s exchange is not available: %s" % (method, self._symm_broken))
+        # The gathered blocks are read by the cutoff / place kernels; every fused key exchange below puts a barrier of the group
+        # after the place kernel, so the next step's broadcasts cannot overtake those reads: no barrier before the broadcasts.
+        pre = symm is None
+        cap, cand, cnt, tot, meta = collect_candidates(
+            st, plan, ops, qp, gp_local, k, stages, idx_offset=idx_offset, rank=self.rank, world=self.world,
+            gather=lambda t: self._gather_small("sample", t, small_nvls, pre))
+        tot_all = self._gather_small("totals", tot, small_nvls, pre)  # [world, bins + 1, Qpad]: per-distance totals + overflow flag
+        # verified inside the place kernel, on every rank from the same gathered data: no list overflowed, and the candidates of ALL
+        # ranks together (a prefix of the global order) number at least min(k, gallery size) for every query
+        bad = torch.zeros(1, dtype=torch.int32, device=qp.device)
+        verify = (meta, bad)
+        _mark(stages)
         if symm is not None and method == "peer_stores":
             # fused place + exchange: a key's global slot is known, so the place kernel stores it straight into that slot of
             # every rank's buffer over NVLink.  Correct, but scattered 8-byte remote stores run at a fraction of the link rate
@@ -804,7 +813,7 @@ class ShardedEvaluator:
                 buf.fill_(EMPTY_KEY)
             hdl.barrier(channel=0)
             st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, None,
-                          peers_dev=int(hdl.buffer_ptrs_dev), npeers=self.world)
+                          peers_dev=int(hdl.buffer_ptrs_dev), npeers=self.world, verify=verify)
             hdl.barrier(channel=1)
             keys = buf.clone() if copy else buf
             _mark(stages)
@@ -816,7 +825,7 @@ class ShardedEvaluator:
             buf, hdl = symm
             hdl.barrier(channel=0)
             buf.fill_(EMPTY_KEY)
-            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf)
+            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf, verify=verify)
             hdl.barrier(channel=1)
             with torch.cuda.device(qp.device):
                 check(_lib.lib().cmh_nvls_allreduce_max_s64(int(hdl.multicast_ptr), buf.numel(), self.rank, self.world, _stream()))
@@ -831,7 +840,7 @@ class ShardedEvaluator:
             # filled + placed before any push lands; all pushes have landed before anyone reads.
             buf, hdl = symm
             buf.fill_(EMPTY_KEY)
-            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf)
+            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, buf, verify=verify)
             hdl.barrier(channel=0)
             with torch.cuda.device(qp.device):
                 check(_lib.lib().cmh_nvls_push_owned_s64(buf.data_ptr(), int(hdl.multicast_ptr), buf.numel(), _stream()))
@@ -840,7 +849,7 @@ class ShardedEvaluator:
             _mark(stages)
         else:
             keys = torch.full((Q, k), EMPTY_KEY, dtype=torch.int64, device=qp.device)
-            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys)
+            st.topk_place(plan, cap, cand, cnt, tot_all, self.world, self.rank, k, idx_offset, keys, verify=verify)
             self._exchange_keys(keys, method)
         return keys, bad
 
@@ -955,11 +964,11 @@ class TopkGraph:
             if self.keys is None:
                 self.keys = torch.empty((plan.Q, k), dtype=torch.int64, device=qp.device)
             st.topk_place(plan, cap, cand, cnt, tot, 1, 0, k, self.idx_offset, self.keys)
-            failed = tot[plan.bins, 0] != 0
+            failed = tot[plan.bins, 0]
         else:
             self.keys, failed = self.ev._topk_candidates(plan, ops, qp, gp, k, self.idx_offset, self.n_geom, self.method, False, None)
-        self.status[0] = failed
-        self.status[1] = self._bad_codes[0]
+        self.status[0:1].copy_(failed.reshape(1))
+        self.status[1:2].copy_(self._bad_codes)
 
     def replay(self) -> torch.Tensor:
         """Queue one step on the current stream; no host synchronisation, no verification (``run`` does both)."""

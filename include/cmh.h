@@ -212,7 +212,11 @@ int cmh_tc_rank_map(const cmh_plan* plan, const cmh_tc_operands* ops, const uint
  *                        stored once through that NVSwitch multicast address (multimem.st) and lands in the same slot of every
  *                        rank's buffer; else with npeers > 0, peer_keys = DEVICE array of npeers buffer addresses (one per rank,
  *                        peer-mapped) and the kernel stores the key into each of them over NVLink; else into `keys`.
- *                        The caller owns the synchronisation (a barrier over the ranks before and after). */
+ *                        The caller owns the synchronisation (a barrier over the ranks before and after).
+ *                        status != NULL (sharded runs): the kernel also verifies the pass from the gathered data — status[0] |= 1
+ *                        when a rank flagged a list overflow (row `bins` of its totals block) or the candidates of all ranks
+ *                        together are fewer than min(k, gallery size) for a query; sample_all = the gathered sample blocks
+ *                        (their header rows carry the shard sizes), same rank_stride = (bins + 1) * Qpad as the totals. */
 int cmh_tc_topk_cutoff(const cmh_plan* sample_plan, const uint32_t* hist_sample, int64_t n_local, int64_t k, int32_t* cutoff,
                        int32_t* ibound, void* stream);
 /* Sharded form of the cutoff: sample_sum = the all-gathered blocks of all ranks, uint32 [world][bins + 1][Qpad]; rank r's block =
@@ -233,7 +237,8 @@ int cmh_tc_topk_count(const cmh_plan* plan, int cand_cap, const uint32_t* cand, 
                       uint32_t* totals, int32_t* flags, void* stream);
 int cmh_tc_topk_place(const cmh_plan* plan, int cand_cap, const uint32_t* cand, const uint32_t* cand_count,
                       const uint32_t* totals_all, int64_t rank_stride, int world, int rank, int64_t k, int64_t idx_offset,
-                      uint64_t* keys, const uint64_t* peer_keys, int npeers, uint64_t* multicast_keys, void* stream);
+                      uint64_t* keys, const uint64_t* peer_keys, int npeers, uint64_t* multicast_keys, const uint32_t* sample_all,
+                      int32_t* status, void* stream);
 
 /* ---- X: the exchange step of the sharded top-k through NVSwitch multicast memory (NVLS) -------------------------------
  * `multicast_ptr` = the multicast address of a symmetric int64 buffer of `count` elements that every rank of the group has

@@ -210,12 +210,25 @@ def test_candidate_stages_global_cutoff_equal_single(world, k):
     assert int(per_query.min()) >= k                                            # together: enough for every query
     assert float(per_query.float().mean()) < 2.5 * k + 200                      # ... and about k of them, not world x k
     keys = torch.full((Q, k), R.EMPTY_KEY, dtype=torch.int64, device=DEV)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
     for r, (plan, lo, cap, cand, cnt, tot) in enumerate(parts):
         mine = torch.full((Q, k), R.EMPTY_KEY, dtype=torch.int64, device=DEV)
-        st.topk_place(plan, cap, cand, cnt, tot_all, world, r, k, lo, mine)
+        st.topk_place(plan, cap, cand, cnt, tot_all, world, r, k, lo, mine, verify=(gathered, status))
         assert int(((mine != R.EMPTY_KEY) & (keys != R.EMPTY_KEY)).sum()) == 0
         keys = torch.maximum(keys, mine)
     assert torch.equal(keys, want)
+    assert int(status.item()) == 0                                              # verified inside the place kernel
+    plan, lo, cap, cand, cnt, tot = parts[0]
+    mine = torch.empty((Q, k), dtype=torch.int64, device=DEV)
+    short = tot_all.clone()
+    short[:, :bins, 5] //= 4                                                    # query 5: a quarter of the candidates -> too few
+    st.topk_place(plan, cap, cand, cnt, short, world, 0, k, lo, mine, verify=(gathered, status))
+    assert int(status.item()) == 1
+    status.zero_()
+    over = tot_all.clone()
+    over[world - 1, bins, 0] = 1                                                # the last rank flagged a list overflow
+    st.topk_place(plan, cap, cand, cnt, over, world, 0, k, lo, mine, verify=(gathered, status))
+    assert int(status.item()) == 1
     with pytest.raises(R.CmhError):                                             # one block instead of the gathered blocks
         st.topk_cutoff_sharded(shards[0][0], gathered[0], k, 0, world)
 
