@@ -380,7 +380,8 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
         if world > 1:
             names = R.TOPK_SHARDED_STAGE_NAMES if len(stage_ms) == 8 else tuple("stage%d" % i for i in range(len(stage_ms)))
         else:
-            names = R.TOPK_FAST_STAGE_NAMES if len(stage_ms) == 7 else R.TOPK_STAGE_NAMES
+            fast = R.candidate_path_ok(st, st.make_plan(Q, N, K, 0), N, k)
+            names = R.TOPK_FAST_STAGE_NAMES if fast else R.TOPK_STAGE_NAMES
         out["stage_ms"] = {"pack": stage_ms[0] / steps, **{n: v / steps for n, v in zip(names, stage_ms[1:])}}
         out["stage_ms_note"] = "measured on the eager step (events cannot be timed inside a graph replay)"
         out["host_ms_per_step"] = host_ms / steps

@@ -375,17 +375,18 @@ class CudaStages:
                                                tot[plan.bins].data_ptr(), _stream()))
         return tot
 
-    def topk_place(self, plan: Plan, cap: int, cand: torch.Tensor, cnt: torch.Tensor, totals_all: torch.Tensor, world: int,
+    def topk_place(self, plan: Plan, cap: int, cand: torch.Tensor, cnt: torch.Tensor, totals_all: Optional[torch.Tensor], world: int,
                    rank: int, k: int, idx_offset: int, keys: Optional[torch.Tensor], peers_dev: Optional[int] = None, npeers: int = 0,
                    multicast: Optional[int] = None, verify: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
                    ) -> Optional[torch.Tensor]:
         """``peers_dev``: device address of a table of ``npeers`` peer-mapped [Q, k] key buffers (one per rank); ``multicast``: the
         NVSwitch multicast address of those buffers.  With either, the keys go straight into every rank's buffer.
         ``verify=(sample_all, status)``: sharded verification inside the same kernel — ``status`` (int32[1]) gets bit 0 set when a
-        rank overflowed a list or the candidates of all ranks are too few (``sample_all`` = the gathered sample blocks)."""
+        rank overflowed a list or the candidates of all ranks are too few (``sample_all`` = the gathered sample blocks).
+        ``totals_all=None`` (one shard): no ``topk_count`` needed, the kernel sums its own per-chunk counts; ``verify=(None, status)``."""
         sample_all, status = verify if verify is not None else (None, None)
         with torch.cuda.device(cand.device):
-            check(_lib.lib().cmh_tc_topk_place(ctypes.byref(plan), cap, cand.data_ptr(), cnt.data_ptr(), totals_all.data_ptr(),
+            check(_lib.lib().cmh_tc_topk_place(ctypes.byref(plan), cap, cand.data_ptr(), cnt.data_ptr(), _ptr(totals_all),
                                                (plan.bins + 1) * plan.Qpad, world, rank, k, idx_offset, _ptr(keys), peers_dev, npeers,
                                                multicast, _ptr(sample_all), _ptr(status), _stream()))
         return keys
@@ -422,14 +423,17 @@ class MapResult:
 
 
 TOPK_STAGE_NAMES = ("expand", "hist_kernel", "scan", "rank_topk_kernel")                       # exact two-pass path
-TOPK_FAST_STAGE_NAMES = ("expand", "sample_hist+cutoff", "collect_kernel", "count", "place")  # candidate path
-TOPK_SHARDED_STAGE_NAMES = ("expand", "sample_hist+cutoff", "collect_kernel", "count", "gather_totals", "place+nvls_allreduce")
+TOPK_FAST_STAGE_NAMES = ("expand", "sample_hist+cutoff", "collect_kernel", "place+verify")     # candidate path, one shard
+TOPK_SHARDED_STAGE_NAMES = ("expand", "sample_hist+cutoff", "collect_kernel", "count", "gather_totals", "place+verify+key_exchange")
 CAND_MIN_ITEMS = 65536   # shards smaller than this take the two-pass path directly
+
+
+SAMPLE_DIV = int(os.environ.get("CMH_SAMPLE_DIV", "16"))   # tuning knob (profiles/README.md): sample = shard / SAMPLE_DIV
 
 
 def candidate_sample(n_local: int) -> int:
     """Size of the gallery prefix whose exact histogram sets the per-query cutoffs: 1/16 of the shard, 4096..65536 items."""
-    return max(4096, min(65536, (n_local // 16) // 512 * 512))
+    return max(4096, min(65536, (n_local // SAMPLE_DIV) // 512 * 512))
 
 
 def candidate_cap(plan: Plan, k: int) -> int:
@@ -447,7 +451,7 @@ def candidate_path_ok(st, plan: Plan, n_local: int, k: int) -> bool:
 
 
 def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None, gather=None, idx_offset: int = 0, rank: int = 0,
-                       world: int = 1):
+                       world: int = 1, count: bool = True):
     """sample histogram -> cutoff -> one tensor-core pass -> per-distance totals (+ fallback flag).
     Returns (cap, cand, cnt, tot, meta).
 
@@ -477,8 +481,10 @@ def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None, gather=
     cap = candidate_cap(plan, k)
     cand, cnt = st.topk_collect(plan, ops, cutoff, cap)
     _mark(stages)
-    tot = st.topk_count(plan, cap, cand, cnt, 0 if gather is not None else k)
-    _mark(stages)
+    tot = None
+    if count:   # (a single shard places straight from the lists: ``topk_place(totals_all=None)``)
+        tot = st.topk_count(plan, cap, cand, cnt, 0 if gather is not None else k)
+        _mark(stages)
     return cap, cand, cnt, tot, meta
 
 
@@ -553,10 +559,11 @@ def topk(qp, gp, nbits: int, k: int, idx_offset: int = 0, target_blocks: int = 0
     ops = st.operands(plan, qp, None, gp, None)
     _mark(stages)
     if exact is not True and candidate_path_ok(st, plan, N, k):
-        cap, cand, cnt, tot, _ = collect_candidates(st, plan, ops, qp, gp, k, stages)
-        st.topk_place(plan, cap, cand, cnt, tot, 1, 0, k, idx_offset, keys)
+        cap, cand, cnt, _, _ = collect_candidates(st, plan, ops, qp, gp, k, stages, count=False)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        st.topk_place(plan, cap, cand, cnt, None, 1, 0, k, idx_offset, keys, verify=(None, status))
         _mark(stages)
-        if int(tot[plan.bins, 0].item()) == 0:     # verified: every cutoff was wide enough and no list overflowed
+        if int(status.item()) == 0:                # verified: every cutoff was wide enough and no list overflowed
             return keys
         if stages is not None:
             del stages[1:]                          # the exact path below re-times its own stages
@@ -627,10 +634,10 @@ def topk_from_host(q_host: torch.Tensor, g_host: torch.Tensor, k: int, device, s
                 plan_s = st.make_plan(Q, n_s, nbits, 0)
                 cutoff = st.topk_cutoff(plan_s, st.hist(plan_s, qp, None, gp[:n_s], None, ops=ops), N, k)
             cand, cnt = st.topk_collect(plan, ops, cutoff, cap, out=None if cand is None else (cand, cnt), chunks=(c0, c1))
-        tot = st.topk_count(plan, cap, cand, cnt, k)
         keys = torch.empty((Q, k), dtype=torch.int64, device=dev)
-        st.topk_place(plan, cap, cand, cnt, tot, 1, 0, k, 0, keys)
-        if int(tot[plan.bins, 0].item()) == 0:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        st.topk_place(plan, cap, cand, cnt, None, 1, 0, k, 0, keys, verify=(None, status))
+        if int(status.item()) == 0:
             return keys
         return topk(qp, gp, nbits, k, exact=True)     # verified-failed: exact two-pass path on the codes that are now resident
 
@@ -960,11 +967,11 @@ class TopkGraph:
         gp = pack_codes(self.g, self._bad_codes)
         ops = st.operands(plan, qp, None, gp, None)
         if self.ev is None:
-            cap, cand, cnt, tot, _ = collect_candidates(st, plan, ops, qp, gp, k)
+            cap, cand, cnt, _, _ = collect_candidates(st, plan, ops, qp, gp, k, count=False)
             if self.keys is None:
                 self.keys = torch.empty((plan.Q, k), dtype=torch.int64, device=qp.device)
-            st.topk_place(plan, cap, cand, cnt, tot, 1, 0, k, self.idx_offset, self.keys)
-            failed = tot[plan.bins, 0]
+            failed = torch.zeros(1, dtype=torch.int32, device=qp.device)
+            st.topk_place(plan, cap, cand, cnt, None, 1, 0, k, self.idx_offset, self.keys, verify=(None, failed))
         else:
             self.keys, failed = self.ev._topk_candidates(plan, ops, qp, gp, k, self.idx_offset, self.n_geom, self.method, False, None)
         self.status[0:1].copy_(failed.reshape(1))

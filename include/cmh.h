@@ -216,7 +216,9 @@ int cmh_tc_rank_map(const cmh_plan* plan, const cmh_tc_operands* ops, const uint
  *                        status != NULL (sharded runs): the kernel also verifies the pass from the gathered data — status[0] |= 1
  *                        when a rank flagged a list overflow (row `bins` of its totals block) or the candidates of all ranks
  *                        together are fewer than min(k, gallery size) for a query; sample_all = the gathered sample blocks
- *                        (their header rows carry the shard sizes), same rank_stride = (bins + 1) * Qpad as the totals. */
+ *                        (their header rows carry the shard sizes), same rank_stride = (bins + 1) * Qpad as the totals.
+ *                        totals_all == NULL (one shard, world = 1; status required): the kernel sums its own per-chunk counts —
+ *                        cmh_tc_topk_count is not needed — and status[0] |= 1 on a list overflow or fewer than min(k, N) candidates. */
 int cmh_tc_topk_cutoff(const cmh_plan* sample_plan, const uint32_t* hist_sample, int64_t n_local, int64_t k, int32_t* cutoff,
                        int32_t* ibound, void* stream);
 /* Sharded form of the cutoff: sample_sum = the all-gathered blocks of all ranks, uint32 [world][bins + 1][Qpad]; rank r's block =
