@@ -153,6 +153,7 @@ PROTOTYPES = {
 _RESTYPES = {"cmh_last_error": ctypes.c_char_p, "cmh_launch_count": ctypes.c_ulonglong, "cmh_encoder_workspace_bytes": ctypes.c_int64,
              "cmh_head_mith_workspace_bytes": ctypes.c_int64}
 
+ABI_VERSION = 2   # CMH_ABI_VERSION of include/cmh.h
 _lib: Optional[ctypes.CDLL] = None
 
 
@@ -167,6 +168,9 @@ def lib() -> ctypes.CDLL:
             except Exception as e:  # no nvcc on the box: use the prebuilt file if there is one
                 if not os.path.exists(SO_PATH):
                     raise CmhError("libcmh.so is missing and cannot be built: %s" % e)
+                import warnings
+
+                warnings.warn("libcmh.so is older than its sources and the rebuild failed (%s): loading the stale build" % e)
         try:
             handle = ctypes.CDLL(path)
         except OSError as e:
@@ -175,8 +179,8 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
-        if handle.cmh_abi_version() != 1:
-            raise CmhError("libcmh.so ABI version mismatch")
+        if handle.cmh_abi_version() != ABI_VERSION:
+            raise CmhError("libcmh.so ABI version %d, this package expects %d (stale build?)" % (handle.cmh_abi_version(), ABI_VERSION))
         _lib = handle
     return _lib
 

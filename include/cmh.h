@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CMH_ABI_VERSION 1
+#define CMH_ABI_VERSION 2   /* 2: round 2 (tensor-core ranking, candidate top-k, multicast exchanges, training tail) */
 
 #define CMH_OK 0
 #define CMH_ERR_INVALID (-1)     /* bad argument (NULL pointer, negative size, misaligned buffer) */

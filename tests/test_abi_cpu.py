@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for n in debug:
         assert hasattr(lib, n), "libcmh.so lacks %s" % n
     assert sorted(_lib.PROTOTYPES) == sorted(names + debug)  # the ctypes table covers both headers exactly
-    assert lib.cmh_abi_version() == 1
+    assert lib.cmh_abi_version() == 2
 
 
 def test_no_torch_or_cuda_driver_link_dependency():
