@@ -340,6 +340,16 @@ class CudaStages:
                                                 cut[1].data_ptr(), _stream()))
         return cut
 
+    def topk_sample_block(self, plan: Plan, plan_s: Optional[Plan], hist_s: Optional[torch.Tensor], idx_offset: int, rank: int,
+                          world: int, device) -> torch.Tensor:
+        """This rank's block of the sharded sample exchange, int32 ``[bins + 1, Qpad]``: per-distance sample counts + the header
+        row ([0] sample items, [1] shard items, [2 + rank] first gallery index).  ``hist_s`` None: an empty shard."""
+        meta = torch.empty((plan.bins + 1, plan.Qpad), dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            check(_lib.lib().cmh_tc_topk_sample_block(ctypes.byref(plan_s) if plan_s is not None else None, _ptr(hist_s), plan.Qpad,
+                                                      plan.bins, plan.N, idx_offset, rank, world, meta.data_ptr(), _stream()))
+        return meta
+
     def topk_cutoff_sharded(self, plan: Plan, sample_sum: torch.Tensor, k: int, rank: int, world: int) -> torch.Tensor:
         """Global cutoff from the gathered sample blocks ``[world, bins + 1, Qpad]`` of all ranks (``collect_candidates``), index
         bound translated into this shard."""
@@ -467,11 +477,7 @@ def collect_candidates(st, plan: Plan, ops, qp, gp, k: int, stages=None, gather=
         hist_s = st.hist(plan_s, qp, None, gp[:n_s], None, ops=ops)
     meta = None
     if gather is not None:
-        meta = torch.empty((plan.bins + 1, plan.Qpad), dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
-            check(_lib.lib().cmh_tc_topk_sample_block(ctypes.byref(plan_s) if plan_s is not None else None, _ptr(hist_s), plan.Qpad,
-                                                      plan.bins, plan.N, idx_offset, rank, world, meta.data_ptr(), _stream()))
-        meta = gather(meta)
+        meta = gather(st.topk_sample_block(plan, plan_s, hist_s, idx_offset, rank, world, dev))
         cutoff = st.topk_cutoff_sharded(plan, meta, k, rank, world)
     elif hist_s is not None:
         cutoff = st.topk_cutoff(plan_s, hist_s, plan.N, k)

@@ -17,8 +17,128 @@ def _u32(t):
 
 
 class OracleStages:
+    """``tensor_cores=True`` additionally offers the stage contracts of the single-pass candidate path (cmh_tc_topk_*), so that
+    ``ShardedEvaluator._topk_candidates`` — gathers, global cutoff, verification, key exchange, fallback — runs over gloo."""
+
+    def __init__(self, tensor_cores=False):
+        self.tensor_cores = tensor_cores
+
     def make_plan(self, Q, N, nbits, ncls, N_geom=None, target_blocks=0):
         return _lib.make_plan(Q, N, nbits, ncls, N_geom, target_blocks or 64)
+
+    # ---- candidate path (numpy restatement of the contracts in include/cmh.h, "Candidate path of the top-k") ----
+    def operands(self, plan, qp, qlp, gp, glp):
+        return (qp, gp) if self.tensor_cores else None
+
+    def topk_sample_block(self, plan, plan_s, hist_s, idx_offset, rank, world, device):
+        out = np.zeros((plan.bins + 1, plan.Qpad), dtype=np.uint32)
+        n_s = 0
+        if hist_s is not None:
+            out[: plan.bins] = (_u32(hist_s).astype(np.int64) & 0xFFFF).sum(axis=0)
+            n_s = plan_s.N
+        out[plan.bins, 0], out[plan.bins, 1], out[plan.bins, 2 + rank] = n_s, plan.N, idx_offset
+        return torch.from_numpy(out.view(np.int32))
+
+    @staticmethod
+    def _cutoff(tot, need, n_items):
+        """T = first distance whose prefix count reaches ``need``; bound = ceil(fraction of bucket T still needed * n_items)."""
+        cum, T, frac, found = 0, len(tot) - 1, 1.0, False
+        for d, t in enumerate(tot):
+            if not found and cum + t >= need:
+                T, found, frac = d, True, (need - cum) / float(t)
+            cum += t
+        return T, (float(np.ceil(frac * n_items)) if found else float(n_items))
+
+    def topk_cutoff(self, plan_s, hist_s, n_local, k):
+        tot = (_u32(hist_s).astype(np.int64) & 0xFFFF).sum(axis=0)            # [bins, Qpad]
+        ks = min(k, n_local) * plan_s.N / float(n_local)
+        need = ks + 5.0 * np.sqrt(ks) + 2.0
+        cut = np.full((2, plan_s.Qpad), -1, dtype=np.int32)
+        for q in range(plan_s.Qpad):
+            T, ib = self._cutoff(tot[:, q], need, n_local)
+            cut[0, q] = T if q < plan_s.Q else -1
+            cut[1, q] = int(min(ib, n_local))
+        return torch.from_numpy(cut)
+
+    def topk_cutoff_sharded(self, plan, sample_all, k, rank, world):
+        s = _u32(sample_all).astype(np.int64)                                 # [world, bins + 1, Qpad]
+        head = s[:, plan.bins]
+        n_sample, n_total = head[:, 0].sum(), head[:, 1].sum()
+        offs = np.array([head[r, 2 + r] for r in range(world)])
+        shard_lo = offs[rank] - offs.min()
+        ks = (min(k, n_total) * n_sample / float(n_total)) if n_total > 0 else 0.0
+        need = ks + 5.0 * np.sqrt(ks) + 2.0
+        tot = s[:, : plan.bins].sum(axis=0)
+        cut = np.full((2, plan.Qpad), -1, dtype=np.int32)
+        for q in range(plan.Qpad):
+            T, ib = self._cutoff(tot[:, q], need, n_total)
+            cut[0, q] = T if q < plan.Q else -1
+            cut[1, q] = int(min(max(ib - shard_lo, -1.0), plan.N))
+        return torch.from_numpy(cut)
+
+    def topk_collect(self, plan, ops, cutoff, cap, out=None, chunks=None):
+        qp, gp = ops
+        cut = cutoff.numpy()
+        cand = np.zeros((plan.nchunks, plan.Qpad, cap), dtype=np.uint32)
+        cnt = np.zeros((plan.nchunks, plan.Qpad), dtype=np.uint32)
+        for c, (lo, hi) in enumerate(self._chunks(plan)):
+            if lo >= hi:
+                continue
+            d, _ = self._dist_rel(qp, None, gp[lo:hi], None)
+            idx = np.arange(lo, hi)
+            for q in range(plan.Q):
+                keep = (d[q] < cut[0, q]) | ((d[q] == cut[0, q]) & (idx <= cut[1, q]))
+                items = np.nonzero(keep)[0]
+                if items.size > cap:
+                    cnt[c, q] = 0xFFFFFFFF
+                    continue
+                cand[c, q, : items.size] = (d[q][items].astype(np.uint32) << 24) | items.astype(np.uint32)
+                cnt[c, q] = items.size
+        return torch.from_numpy(cand.view(np.int32)), torch.from_numpy(cnt.view(np.int32))
+
+    def topk_count(self, plan, cap, cand, cnt, k):
+        ca, cn = _u32(cand), _u32(cnt)
+        tot = np.zeros((plan.bins + 1, plan.Qpad), dtype=np.uint32)
+        need = min(k, plan.N)
+        for q in range(plan.Q):
+            for c in range(plan.nchunks):
+                if cn[c, q] == 0xFFFFFFFF:
+                    tot[plan.bins, 0] |= 1
+                    continue
+                tot[: plan.bins, q] += np.bincount(ca[c, q, : cn[c, q]] >> 24, minlength=plan.bins).astype(np.uint32)
+            if k > 0 and tot[: plan.bins, q].sum() < need:
+                tot[plan.bins, 0] |= 1
+        return torch.from_numpy(tot.view(np.int32))
+
+    def topk_place(self, plan, cap, cand, cnt, totals_all, world, rank, k, idx_offset, keys, peers_dev=None, npeers=0,
+                   multicast=None, verify=None):
+        ca, cn = _u32(cand), _u32(cnt)
+        out = keys.numpy().view(np.uint64)
+        if totals_all is None:
+            local = _u32(self.topk_count(plan, cap, cand, cnt, 0))
+            t = local[None].astype(np.int64)
+        else:
+            t = _u32(totals_all).astype(np.int64)                             # [world, bins + 1, Qpad]
+        sample_all, status = verify if verify is not None else (None, None)
+        if status is not None:
+            n_total = plan.N if sample_all is None else int(_u32(sample_all).astype(np.int64)[:, plan.bins, 1].sum())
+            if t[:, plan.bins, 0].max() != 0 or (t[:, : plan.bins, : plan.Q].sum(axis=(0, 1)) < min(k, n_total)).any():
+                status |= 1
+        alls = t[:, : plan.bins].sum(axis=0)
+        below = np.cumsum(alls, axis=0) - alls + t[:rank, : plan.bins].sum(axis=0)
+        for q in range(plan.Q):
+            run = below[:, q].copy()
+            for c in range(plan.nchunks):
+                if cn[c, q] == 0xFFFFFFFF:
+                    continue
+                first = idx_offset + c * plan.chunk_items
+                for e in ca[c, q, : cn[c, q]]:
+                    d = int(e >> 24)
+                    r = run[d]
+                    run[d] += 1
+                    if r < k:
+                        out[q, r] = (np.uint64(d) << np.uint64(32)) | np.uint64(first + int(e & 0xFFFFFF))
+        return keys
 
     @staticmethod
     def _chunks(plan):
@@ -32,7 +152,7 @@ class OracleStages:
         rel = ((_u32(qlp)[:, None, :] & _u32(glp)[None, :, :]) != 0).any(axis=2)
         return d, rel
 
-    def hist(self, plan, qp, qlp, gp, glp):
+    def hist(self, plan, qp, qlp, gp, glp, ops=None):
         out = np.zeros((plan.nchunks, plan.bins, plan.Qpad), dtype=np.uint32)
         for c, (lo, hi) in enumerate(self._chunks(plan)):
             if lo >= hi:
@@ -106,7 +226,7 @@ class OracleStages:
         below = np.concatenate(([0], np.cumsum(hist)[:-1]))
         return ranks - below[drow]
 
-    def rank_map(self, plan, qp, qlp, gp, glp, sc, tindex=None, n_total=None):
+    def rank_map(self, plan, qp, qlp, gp, glp, sc, tindex=None, n_total=None, ops=None):
         ap = np.zeros((plan.nchunks, plan.Qpad), dtype=np.float64)
         wa, wr = sc["within_all"].numpy(), sc["within_rel"].numpy()
         ba, br = sc["below_all"].numpy(), sc["below_rel"].numpy()
@@ -144,7 +264,7 @@ class OracleStages:
             ap = parts[:, : plan.Q].sum(axis=0) / total.numpy()[: plan.Q].astype(np.float64)
         return torch.from_numpy(ap), torch.tensor(ap.sum() / plan.Q, dtype=torch.float64)
 
-    def rank_topk(self, plan, qp, gp, sc, k, idx_offset, keys=None):
+    def rank_topk(self, plan, qp, gp, sc, k, idx_offset, keys=None, ops=None):
         out = np.full((plan.Q, k), EMPTY, dtype=np.uint64)
         wa, ba, th = sc["within_all"].numpy(), sc["below_all"].numpy(), sc["thresh"].numpy()
         for c, (lo, hi) in enumerate(self._chunks(plan)):

@@ -73,6 +73,78 @@ def test_sharded_evaluator_over_gloo(tmp_path, world, name):
         assert torch.equal(o["keys"], outs[0]["keys"]) and o["map"] == outs[0]["map"]  # every rank agrees
 
 
+def _candidate_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from clip_based_cross_modal_hash_b200 import retrieval as R
+        from oracle import hamming_oracle as ho
+        from tests._oracle_stages import OracleStages
+
+        Q, K, k = 6, 32, 300
+        N = 70_000 * world + 13                                   # shards above the candidate path's minimum size, ragged tail
+        g = torch.Generator().manual_seed(7)
+        qB = torch.randint(0, 2, (Q, K), generator=g).float() * 2 - 1
+        rB = torch.randint(0, 2, (N, K), generator=g).float() * 2 - 1
+        qp = torch.from_numpy(ho.pack_codes(qB.numpy()).view(np.int32))
+        gp = torch.from_numpy(ho.pack_codes(rB.numpy()).view(np.int32))
+        bounds = R.shard_bounds(N, world)
+        lo, hi = bounds[rank]
+        st = OracleStages(tensor_cores=True)
+        calls = {"collect": 0, "rank_topk": 0}
+        collect, rank_topk = st.topk_collect, st.rank_topk
+        st.topk_collect = lambda *a, **kw: (calls.__setitem__("collect", calls["collect"] + 1), collect(*a, **kw))[1]
+        st.rank_topk = lambda *a, **kw: (calls.__setitem__("rank_topk", calls["rank_topk"] + 1), rank_topk(*a, **kw))[1]
+        ev = R.ShardedEvaluator(stages=st)
+        keys = ev.topk(qp, gp[lo:hi], K, k, lo)                  # candidate path: gathers, global cutoff, verification, MAX exchange
+        took_candidates = calls == {"collect": 1, "rank_topk": 0}
+        exact = ev.topk(qp, gp[lo:hi], K, k, lo, exact=True)
+        # a gallery whose sample prefixes say nothing about the rest: queries 0/1 have 5 000 exact copies at the END of every shard
+        rB2 = rB.clone()
+        for a, b in bounds:
+            rB2[b - 5000:b] = qB[0]
+        gp2 = torch.from_numpy(ho.pack_codes(rB2.numpy()).view(np.int32))
+        calls.update(collect=0, rank_topk=0)
+        keys2 = ev.topk(qp, gp2[lo:hi], K, k, lo)
+        fell_back = calls["collect"] == 1 and calls["rank_topk"] == 1
+        torch.save({"keys": keys, "exact": exact, "keys2": keys2, "took_candidates": took_candidates, "fell_back": fell_back},
+                   os.path.join(out_dir, "c%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def _stable_topk_keys(qB, rB, k):
+    d = ((qB.shape[1] - qB.double() @ rB.double().t()) / 2).round().to(torch.int64)
+    idx = torch.argsort(d, dim=1, stable=True)[:, :k]
+    return (torch.gather(d, 1, idx) << 32) | idx
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_candidate_topk_over_gloo(tmp_path, world):
+    """the single-pass candidate path of the sharded top-k, host logic over gloo with the numpy stage stand-in: sample blocks
+    gathered -> one global cutoff -> collect / count -> totals gathered -> verification -> placement -> MAX exchange; and a gallery
+    with unrepresentative prefixes is caught by the verification on every rank and re-done by the exact path."""
+    mp.spawn(_candidate_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    Q, K, k = 6, 32, 300
+    N = 70_000 * world + 13
+    g = torch.Generator().manual_seed(7)
+    qB = torch.randint(0, 2, (Q, K), generator=g).float() * 2 - 1
+    rB = torch.randint(0, 2, (N, K), generator=g).float() * 2 - 1
+    want = _stable_topk_keys(qB, rB, k)
+    from clip_based_cross_modal_hash_b200 import retrieval as R
+
+    rB2 = rB.clone()
+    for a, b in R.shard_bounds(N, world):
+        rB2[b - 5000:b] = qB[0]
+    want2 = _stable_topk_keys(qB, rB2, k)
+    for r in range(world):
+        o = torch.load(os.path.join(str(tmp_path), "c%d.pt" % r))
+        assert o["took_candidates"] and o["fell_back"]
+        assert torch.equal(o["keys"], want) and torch.equal(o["exact"], want)
+        assert torch.equal(o["keys2"], want2)
+
+
 def _merge_worker(rank, world, port, out):
     import torch.distributed as dist
 
