@@ -664,10 +664,15 @@ TOPK_EXCHANGES = ("auto", "nvls", "nvls_reduce", "peer_stores", "rank_scatter", 
 class ShardedEvaluator:
     """mAP / top-k with the gallery sharded over ``group``; queries (and their labels) are replicated.
 
-    Exchange steps (all ``all_gather_into_tensor``; NCCL over NVLink on GPUs, gloo in the CPU tests):
-      mAP    : per-shard bucket totals [2, bins, Qpad] int32  ->  scan  ->  per-chunk AP partials fp64
-      top-k  : per-shard bucket totals -> every item's global rank -> ONE all-reduce(MAX) of the [Q, k] key buffer
-               (or, method="allgather_merge": per-shard partial top-k keys, ONE all-gather, merge kernel)
+    Exchange steps:
+      mAP    : per-shard bucket totals [2, bins, Qpad] int32 (all-gather)  ->  scan  ->  ONE fp64 AP partial per query (all-gather)
+      top-k  : candidate path (default, large shards): sample blocks gathered -> ONE global cutoff per query -> collect / count ->
+               candidate totals gathered -> place + verify -> every rank pushes the [Q, k] slots it owns to all ranks.  On a box
+               with NVSwitch multicast memory all three exchanges are store kernels on the multicast address between device-side
+               barriers (`cmh_exchange.cu`), otherwise all_gather_into_tensor / all_reduce(MAX) (NCCL; gloo in the CPU tests)
+               exact two-pass path (small shards, failed verification, ``exact=True``): per-shard bucket totals -> every item's
+               global rank -> ONE all-reduce(MAX) of the [Q, k] key buffer (or, method="allgather_merge": per-shard partial top-k
+               keys, ONE all-gather, merge kernel)
     Every rank ends with the identical result.
     """
 
@@ -870,12 +875,16 @@ class ShardedEvaluator:
              method: str = "auto", exact: Optional[bool] = None, copy: bool = True, stages: Optional[list] = None) -> torch.Tensor:
         """Global top-k keys [Q, k] (identical on every rank) of a gallery sharded by contiguous index range.
 
-        ``rank_scatter`` (default): the counting formulation gives every item its GLOBAL stable rank from this rank's own
-        histogram plus the other ranks' per-bucket totals (one 2*bins*Qpad*4-byte all-gather, 2.6 MB at 10k queries x 64 bit),
-        so each rank writes its items straight into their final slots of a [Q, k] buffer (untouched slots stay EMPTY = -1) and
-        ONE all-reduce(MAX) of that buffer (80 MB at C4) finishes the job — no partial lists, no merge kernel.
-        ``allgather_merge``: BASELINE.json's literal exchange — per-shard partial top-k, one all-gather of [Q, k] keys per rank
-        (8 x 80 MB at C4), merge kernel.  Both are exact and give the same keys (tests/test_sharded_gloo.py, check_multi_gpu.py).
+        ``method`` names the exchange of the result keys (TOPK_EXCHANGES):
+        ``auto`` / ``nvls``: candidate path with the multicast exchanges (`_topk_candidates`); ``auto`` falls back to the NCCL
+        exchanges when the group has no multicast memory, ``nvls`` raises.  ``nvls_reduce`` / ``peer_stores``: alternative fused key
+        exchanges (reduction inside the switch / per-key stores into every peer), kept for comparison.
+        ``rank_scatter``: NCCL all-reduce(MAX) of the [Q, k] buffer in which every rank filled the slots it owns — the counting
+        formulation gives every item its GLOBAL stable rank from this rank's own counts plus the other ranks' per-bucket totals, so
+        there are no partial lists and no merge.  ``allgather_merge``: BASELINE.json's literal exchange — per-shard partial top-k,
+        one all-gather of [Q, k] keys per rank (8 x 80 MB at C4), merge kernel; always the exact two-pass path.
+        All are exact and give the same keys (tests/test_sharded_gloo.py, scripts/check_multi_gpu.py).  ``copy=False`` returns the
+        symmetric result buffer itself (valid until the next call).
         """
         st = self.stages
         k = _check_k(k)
