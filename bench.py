@@ -310,13 +310,17 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
 
     # The timed step is ONE CUDA-graph replay of pack -> ... -> place (retrieval.TopkGraph) + its status read-back; the same step
     # queued eagerly, launch by launch, is timed afterwards for the per-stage breakdown and the host cost it carries.
-    graph = None
+    graph, graph_error = None, None
     if not args.no_graph:
         try:
             graph = R.TopkGraph(d_qB, d_rB, k, evaluator=ev, idx_offset=lo if world > 1 else 0,
                                 n_geom=n_geom if world > 1 else None, method=args.topk_exchange)
         except R.CmhError:
             graph = None           # shape outside the candidate path (decided on the common geometry: same on every rank)
+        except Exception as e:     # capture refused by this driver / NCCL build: time the eager step instead, and say so
+            graph, graph_error = None, "%s: %s" % (type(e).__name__, str(e)[:200])
+        if D.all_max(0.0 if graph is not None else 1.0) != 0.0:
+            graph = None           # every rank replays, or none does
 
     def timed(fn, with_stages):
         for _ in range(max(warmup, 3)):
@@ -363,6 +367,8 @@ def bench_topk(args, D, cfg, name, steps, warmup, peaks, scaling, want_e2e=True,
     out = {"bits": K, "ms_per_step": total_ms / steps, "value": Q * n_total * steps / (total_ms * 1e-3), "steps": steps,
            "clocks": clocks.summary(), "gpu_launches": n_launch,
            "step": "one CUDA-graph replay + status read-back" if graph is not None else "eager launches"}
+    if graph_error is not None:
+        out["graph_error"] = graph_error
     if graph is not None:
         out["graph"] = {"kernels_per_replay": graph.kernels, "host_ms_per_step_incl_status_wait": graph_host_ms / steps}
         if eager_ms is not None:
@@ -751,7 +757,7 @@ def run_ours(args, cfg, name):
     if args.op == "topk":
         line["exchange"] = {"method": args.topk_exchange, **head.get("exchange_info", {})} if world > 1 else None
         line["parity_check"] = head.get("parity_check")
-        for key in ("step", "graph", "eager_ms_per_step", "stage_ms_note"):
+        for key in ("step", "graph", "graph_error", "eager_ms_per_step", "stage_ms_note"):
             if key in head:
                 line[key] = head[key]
         dom, dom_ms = None, None
