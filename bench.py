@@ -779,6 +779,9 @@ def run_ours(args, cfg, name):
                     "65 %, tensor pipe (UTCIMMA) 16.8 %, DRAM 1 %; traffic = dram bytes read + written per launch at C4-64 "
                     "(applies to the 64-bit headline only)",
             "survey_8d": s8,
+            "frac_survey_8d": s8["achieved"],
+            "binding_pipe": {"pipe": "alu (integer)", "busy_pct_ncu": 80.8, "kernel": "tc_rank_kernel<64,0,COLLECT>",
+                             "source": "profiles/r2_ncu_topk_C4-64.txt (ncu --set full, C4-64, 1 GPU; not re-measured by this run)"},
         }
     else:
         line["stage_ms"] = head.get("stage_ms")
