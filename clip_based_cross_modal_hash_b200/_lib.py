@@ -43,13 +43,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not any(os.access(os.path.join(p, nvcc), os.X_OK) for p in os.environ.get("PATH", "").split(os.pathsep)):
         if os.path.exists("/usr/local/cuda/bin/nvcc"):
             nvcc = "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC] + sources() + ["-o", SO_PATH + ".tmp"]
+    tmp = "%s.tmp.%d" % (SO_PATH, os.getpid())   # per process: ranks of one torchrun launch may all find the library stale
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC] + sources() + ["-o", tmp]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-8000:]))
-    os.replace(SO_PATH + ".tmp", SO_PATH)
+    os.replace(tmp, SO_PATH)
     if verbose:
         print(res.stderr)
     return SO_PATH
